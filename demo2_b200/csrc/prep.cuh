@@ -1,0 +1,57 @@
+// Operand preparation for the split-fp16 distance GEMM.
+//
+// Every fp32 feature row x is (optionally L2-normalised, then) scaled by an exact power of
+// two s = 2^e so that max|x*s| lies in [2^14, 2^15), and split into two fp16 numbers
+//   hi = fp16(x*s),  lo = fp16(x*s - hi)          (x*s = hi + lo up to 2^-22 relative)
+// The tensor cores then accumulate hi*hi + hi*lo + lo*hi in fp32 (3 fp16 MMA passes, the
+// fp16 analogue of 3xTF32 at twice the MMA rate) and the epilogue undoes the scaling with
+// the exact factors 2^-e_a * 2^-e_b.
+#pragma once
+
+#include "common.cuh"
+
+namespace demo {
+
+// View of a prepared operand (device pointers into a caller-owned buffer).
+struct PrepView {
+  __half* hi = nullptr;       // [rows][pitch] fp16
+  __half* lo = nullptr;       // [rows][pitch] fp16
+  float* norm = nullptr;      // [rows]  sum x^2 (after the optional normalisation), fp32
+  float* inv_scale = nullptr; // [rows]  2^-e
+  int rows = 0, d = 0, pitch = 0;
+};
+
+inline int prep_pitch(int d) { return round_up(d, 64); }
+
+// Bytes of a prepared operand and its carve-up (same function sizes and slices).
+inline size_t prep_carve(Carver& c, int rows, int d, PrepView* v) {
+  PrepView t;
+  t.rows = rows;
+  t.d = d;
+  t.pitch = prep_pitch(d);
+  size_t r = static_cast<size_t>(rows > 0 ? rows : 1);
+  t.hi = c.take<__half>(r * t.pitch);
+  t.lo = c.take<__half>(r * t.pitch);
+  t.norm = c.take<float>(r);
+  t.inv_scale = c.take<float>(r);
+  if (v) *v = t;
+  return c.off;
+}
+inline size_t prep_bytes(int rows, int d) {
+  Carver c(nullptr, ~size_t(0));
+  return round_up(prep_carve(c, rows, d, nullptr), size_t(1024));
+}
+
+enum : int {
+  PREP_NORM_NONE = 0,
+  PREP_NORM_F_NORMALIZE = 1,  // x / max(|x|, 1e-12)   (utils/metrics.py:345)
+  PREP_NORM_TRIPLET = 2,      // x / (|x| + 1e-12)     (layers/triplet_loss.py:12)
+};
+
+// perm (optional): output row r is input row perm[r].  xn_out (optional): normalised fp32 rows
+// written in OUTPUT order.
+int launch_prep_rows(const float* x, int rows, int d, long long ldx, int norm_mode,
+                     const int* perm, const PrepView& out, float* xn_out, long long ldxn,
+                     cudaStream_t stream);
+
+}  // namespace demo

@@ -1,0 +1,38 @@
+"""Shared test helpers: seeded cases (inputs are regenerated, never stored)."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from demo2_b200 import synth  # noqa: E402
+from oracle import reid_oracle as oracle  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def make_case(shape: str, seed: int, sigma: float, gallery_is_query: bool = False):
+    """Returns (qf, gf, q_pids, g_pids, q_camids, g_camids) with qf/gf L2-normalised by
+    the oracle's numpy normalisation (bit-reproducible across hosts)."""
+    s = synth.make_named(shape, sigma=sigma, seed=seed)
+    qf = oracle.l2_normalize(s.qf.numpy())
+    if gallery_is_query:
+        return qf, qf.copy(), s.q_pids, s.q_pids.copy(), s.q_camids, s.q_camids.copy()
+    gf = oracle.l2_normalize(s.gf.numpy())
+    return qf, gf, s.q_pids, s.g_pids, s.q_camids, s.g_camids
+
+
+def sample_index(n_rows: int, n_cols: int, count: int = 4096):
+    """Deterministic scattered sample of a matrix (flat indices)."""
+    total = n_rows * n_cols
+    step = max(1, total // count)
+    return np.arange(0, total, step, dtype=np.int64)[:count]
+
+
+def load_golden(name: str):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
