@@ -212,16 +212,20 @@ def test_eval_edge_cases():
     gp, gc = np.array([7, 9, 7, 8]), np.array([0, 1, 1, 1])
     # q0: gallery 0 is junk (same pid+cam); order 2,1,3 -> positive {2} at rank 1 -> AP 1
     # q1: order 1,2,3,0 -> positive {3} at rank 3 -> AP 1/3
-    cmc, mAP = oracle.eval_func(dist, qp, gp, qc, gc, max_rank=50)
-    assert cmc.shape == (4,)  # gallery smaller than max_rank (:118-120)
-    np.testing.assert_allclose(cmc, [0.5, 0.5, 1.0, 1.0])
+    # (with junk removed the kept lists have different lengths, so -- like the reference,
+    # whose np.asarray(all_cmc) is ragged then -- max_rank must not exceed the shortest list)
+    cmc, mAP = oracle.eval_func(dist, qp, gp, qc, gc, max_rank=3)
+    np.testing.assert_allclose(cmc, [0.5, 0.5, 1.0])
     assert abs(mAP - (1 + 1 / 3) / 2) < 1e-12
+    # gallery smaller than max_rank shrinks max_rank (:118-120)
+    cmc, mAP = oracle.eval_func(dist, qp, gp, np.array([5, 5]), gc, max_rank=50)
+    assert cmc.shape == (4,)
     # a query whose identity is absent is skipped (:142-144)
-    cmc, mAP = oracle.eval_func(dist, np.array([7, 5]), gp, qc, gc)
-    np.testing.assert_allclose(cmc, [1, 1, 1, 1])
+    cmc, mAP = oracle.eval_func(dist, np.array([7, 5]), gp, qc, gc, max_rank=3)
+    np.testing.assert_allclose(cmc, [1, 1, 1])
     assert mAP == 1.0
     with pytest.raises(AssertionError):
-        oracle.eval_func(dist, np.array([5, 5]), gp, qc, gc)
+        oracle.eval_func(dist, np.array([5, 5]), gp, qc, gc, max_rank=3)
     # exact ties -> ascending gallery index
     dist = np.array([[1, 1, 1, 1]], np.float32)
     ofs, idx, r, c = oracle.rank_counts(dist, np.array([1]), np.array([0, 1, 0, 1]),
