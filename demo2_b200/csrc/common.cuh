@@ -11,20 +11,13 @@
 #include <cstdio>
 #include <cstring>
 
+#include "../../include/demo_b200.h"  // error codes + public flags
+
 namespace demo {
 
 // ----------------------------------------------------------------------------------
 // error plumbing (C ABI: int return code + thread-local message)
 // ----------------------------------------------------------------------------------
-enum : int {
-  DEMO_OK = 0,
-  DEMO_ERR_INVALID = -1,    // bad argument
-  DEMO_ERR_CUDA = -2,       // CUDA runtime / driver error
-  DEMO_ERR_WORKSPACE = -3,  // workspace too small
-  DEMO_ERR_UNSUPPORTED = -4,
-  DEMO_ERR_CAPACITY = -5,   // caller-provided capacity exceeded
-};
-
 void set_error(const char* fmt, ...);
 const char* last_error();
 
@@ -34,7 +27,7 @@ const char* last_error();
     if (_e != cudaSuccess) {                                                           \
       ::demo::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
                         cudaGetErrorString(_e));                                       \
-      return ::demo::DEMO_ERR_CUDA;                                                    \
+      return DEMO_ERR_CUDA;                                                    \
     }                                                                                  \
   } while (0)
 
@@ -42,14 +35,14 @@ const char* last_error();
   do {                                                                                 \
     if (!(cond)) {                                                                     \
       ::demo::set_error(__VA_ARGS__);                                                  \
-      return ::demo::DEMO_ERR_INVALID;                                                 \
+      return DEMO_ERR_INVALID;                                                 \
     }                                                                                  \
   } while (0)
 
 #define DEMO_TRY(expr)                                                                 \
   do {                                                                                 \
     int _r = (expr);                                                                   \
-    if (_r != ::demo::DEMO_OK) return _r;                                              \
+    if (_r != DEMO_OK) return _r;                                              \
   } while (0)
 
 constexpr int kNumSMsB200 = 148;

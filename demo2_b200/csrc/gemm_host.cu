@@ -1,0 +1,112 @@
+// Host side of the tcgen05 distance GEMM: TMA tensor maps, schedules, and the SIMT (FFMA)
+// reference kernel used as an on-device self-check of the tensor-core path.
+#include <cstdarg>
+
+#include "gemm_epilogues.cuh"
+
+namespace demo {
+
+// ---------------------------------------------------------------------------------------
+// error string
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ---------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched through the runtime: no libcuda link needed)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_operand_tensor_map(CUtensorMap* map, const __half* base, int rows, int d, int pitch,
+                            int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
+    return DEMO_ERR_CUDA;
+  }
+  DEMO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && pitch % 8 == 0,
+               "operand not 16-byte aligned (base %p pitch %d)", (const void*)base, pitch);
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows > 0 ? rows : 1)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch) * sizeof(__half)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d d %d pitch %d)", (int)r, rows, d, pitch);
+    return DEMO_ERR_CUDA;
+  }
+  return DEMO_OK;
+}
+
+int make_gemm_operands(const PrepView& a, const PrepView& b, GemmOperands* ops) {
+  DEMO_REQUIRE(a.d == b.d, "operand feature dims differ (%d vs %d)", a.d, b.d);
+  DEMO_TRY(make_operand_tensor_map(&ops->a_hi, a.hi, a.rows, a.d, a.pitch, kBM));
+  DEMO_TRY(make_operand_tensor_map(&ops->a_lo, a.lo, a.rows, a.d, a.pitch, kBM));
+  DEMO_TRY(make_operand_tensor_map(&ops->b_hi, b.hi, b.rows, b.d, b.pitch, kBN));
+  DEMO_TRY(make_operand_tensor_map(&ops->b_lo, b.lo, b.rows, b.d, b.pitch, kBN));
+  ops->num_k_blocks = ceil_div(a.d, kBK);
+  return DEMO_OK;
+}
+
+Schedule make_dense_schedule(int M, int N) {
+  Schedule s;
+  s.mode = 0;
+  s.M = M;
+  s.N = N;
+  s.m_blocks = ceil_div(M, kBM);
+  s.n_tiles = ceil_div(N, kBN);
+  s.group_n = 8;
+  s.num_units = s.m_blocks * s.n_tiles;
+  return s;
+}
+
+Schedule make_chunked_schedule(int M, int N, int chunk_tiles) {
+  Schedule s;
+  s.mode = 1;
+  s.M = M;
+  s.N = N;
+  s.m_blocks = ceil_div(M, kBM);
+  s.n_tiles = ceil_div(N, kBN);
+  s.chunk_tiles = chunk_tiles < 1 ? 1 : chunk_tiles;
+  s.n_chunks = ceil_div(s.n_tiles, s.chunk_tiles);
+  s.group_m = 16;
+  s.num_units = s.m_blocks * s.n_chunks;
+  return s;
+}
+
+Schedule make_list_schedule(int M, int N, const int4* list, const int* list_count) {
+  Schedule s;
+  s.mode = 2;
+  s.M = M;
+  s.N = N;
+  s.m_blocks = ceil_div(M, kBM);
+  s.n_tiles = ceil_div(N, kBN);
+  s.list = list;
+  s.list_count = list_count;
+  return s;
+}
+
+}  // namespace demo

@@ -1,0 +1,288 @@
+// Persistent, warp-specialised tcgen05 distance GEMM for sm_100a.
+//
+//   acc[m][n] = sum_k  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (fp16 operands, fp32 TMEM accumulator)
+//   dot[m][n] = acc * 2^-ea[m] * 2^-eb[n]                          (exact power-of-two rescale)
+//
+// Operands are the prepared fp16 hi/lo rows of prep.cuh (K-major, 64-byte swizzled tiles loaded
+// by TMA).  Warp roles per CTA (256 threads, one CTA per SM):
+//   warp 0  TMA producer       (4 tile loads per k-block: A_hi, A_lo, B_hi, B_lo)
+//   warp 1  MMA issuer         (3 x BK/16 tcgen05.mma per k-block, one thread)
+//   warp 2  TMEM allocator
+//   warps 4-7  epilogue        (thread t of warp w owns accumulator row 32*(w%4)+t)
+// The 128 x 256 fp32 accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue
+// of tile i overlaps the MMAs of tile i+1.  What the epilogue does with the distances is a
+// policy class (store / rank-count / extract-positives / hard-mining), see gemm_epilogues.cuh.
+#pragma once
+
+#include "common.cuh"
+#include "prep.cuh"
+
+namespace demo {
+
+constexpr int kBM = 128;            // rows of A per tile (TMEM lanes)
+constexpr int kBN = 256;            // rows of B per tile (TMEM columns)
+constexpr int kBK = 32;             // fp16 elements per k-block = 64 B = one SWIZZLE_64B span
+constexpr int kUmmaK = 16;          // K per tcgen05.mma (kind::f16)
+constexpr int kTileABytes = kBM * kBK * 2;
+constexpr int kTileBBytes = kBN * kBK * 2;
+constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // 48 KB
+constexpr int kGemmThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kTmemCols = 2 * kBN;  // 512: double-buffered accumulator
+
+// One unit of work: a fixed block of 128 A rows against `n_rows` consecutive B rows
+// starting at n0 (processed as ceil(n_rows / kBN) tiles by the same CTA).
+struct WorkUnit {
+  int m0, n0, n_rows, index;
+};
+
+// How units are enumerated.  All three roles of a CTA walk the same sequence.
+struct Schedule {
+  int mode = 0;          // 0: dense tiles, n-grouped raster; 1: chunked rows of tiles; 2: device list
+  int M = 0, N = 0;      // valid rows of A / B
+  int m_blocks = 0, n_tiles = 0;
+  int group_n = 8;       // mode 0: n-tiles per raster group
+  int chunk_tiles = 1;   // mode 1: n-tiles per unit
+  int n_chunks = 0;      // mode 1
+  int group_m = 16;      // mode 1: m-blocks that share a chunk consecutively
+  int num_units = 0;     // modes 0/1
+  const int4* list = nullptr;      // mode 2: (m_block, n0, n_rows, _)
+  const int* list_count = nullptr; // mode 2: device-side unit count
+};
+
+__device__ __forceinline__ int schedule_num_units(const Schedule& s) {
+  return s.mode == 2 ? __ldg(s.list_count) : s.num_units;
+}
+
+__device__ __forceinline__ WorkUnit schedule_get(const Schedule& s, int u) {
+  WorkUnit w;
+  w.index = u;
+  if (s.mode == 0) {
+    const int per_group = s.group_n * s.m_blocks;
+    const int g = u / per_group, r = u - g * per_group;
+    const int n_in = min(s.group_n, s.n_tiles - g * s.group_n);
+    const int m = r / n_in, n = g * s.group_n + (r - m * n_in);
+    w.m0 = m * kBM;
+    w.n0 = n * kBN;
+    w.n_rows = min(kBN, s.N - w.n0);
+  } else if (s.mode == 1) {
+    const int per_group = s.group_m * s.n_chunks;
+    const int g = u / per_group, r = u - g * per_group;
+    const int m_in = min(s.group_m, s.m_blocks - g * s.group_m);
+    const int c = r / m_in, m = g * s.group_m + (r - c * m_in);
+    w.m0 = m * kBM;
+    w.n0 = c * s.chunk_tiles * kBN;
+    w.n_rows = min(s.chunk_tiles * kBN, s.N - w.n0);
+  } else {
+    const int4 e = __ldg(s.list + u);
+    w.m0 = e.x * kBM;
+    w.n0 = e.y;
+    w.n_rows = e.z;
+  }
+  return w;
+}
+
+struct TileInfo {
+  int m0, n0, n_valid;   // n_valid: valid columns in this tile (<= kBN)
+  int unit_index;
+  bool first_in_unit, last_in_unit;
+};
+
+template <class Epi>
+struct GemmSmem {
+  static constexpr int kStages = Epi::kStages;
+  static constexpr int kBarrierBytes = 8 * (2 * kStages + 4) + 16;
+  static constexpr int kEpiOffset = kStages * kStageBytes + round_up(kBarrierBytes, 128);
+  static constexpr int kTotal = kEpiOffset + Epi::kSmemBytes + 1024;  // + alignment slack
+};
+
+template <class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const Schedule sched, const int num_k_blocks, const typename Epi::Params ep) {
+  constexpr int kStages = Epi::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* bar_empty = bar_full + kStages;
+  uint64_t* bar_tfull = bar_empty + kStages;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint8_t* epi_smem = smem + GemmSmem<Epi>::kEpiOffset;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_tfull[s], 1);
+      mbar_init(&bar_tempty[s], kEpiThreads / 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_units = schedule_num_units(sched);
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const WorkUnit w = schedule_get(sched, u);
+        for (int n_off = 0; n_off < w.n_rows; n_off += kBN) {
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            mbar_wait(&bar_empty[stage], phase ^ 1u);
+            uint8_t* st = smem + stage * kStageBytes;
+            mbar_expect_tx(&bar_full[stage], kStageBytes);
+            tma_load_2d(st, &tm_a_hi, &bar_full[stage], kb * kBK, w.m0);
+            tma_load_2d(st + kTileABytes, &tm_a_lo, &bar_full[stage], kb * kBK, w.m0);
+            tma_load_2d(st + 2 * kTileABytes, &tm_b_hi, &bar_full[stage], kb * kBK, w.n0 + n_off);
+            tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &tm_b_lo, &bar_full[stage], kb * kBK,
+                        w.n0 + n_off);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kBM, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const WorkUnit w = schedule_get(sched, u);
+        for (int n_off = 0; n_off < w.n_rows; n_off += kBN) {
+          mbar_wait(&bar_tempty[as], aphase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * kBN);
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+            const uint64_t a_hi = make_kmajor_desc<kBK * 2>(sa);
+            const uint64_t a_lo = make_kmajor_desc<kBK * 2>(sa + kTileABytes);
+            const uint64_t b_hi = make_kmajor_desc<kBK * 2>(sa + 2 * kTileABytes);
+            const uint64_t b_lo = make_kmajor_desc<kBK * 2>(sa + 2 * kTileABytes + kTileBBytes);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);  // +32 B per step
+              // small cross terms first, then the main term
+              umma_f16(tmem_acc, a_hi + adv, b_lo + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(tmem_acc, a_lo + adv, b_hi + adv, idesc, 1u);
+              umma_f16(tmem_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
+            umma_commit(&bar_empty[stage]);  // frees the smem stage once these MMAs retire
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(&bar_tfull[as]);  // accumulator complete -> epilogue
+          if (++as == 2) {
+            as = 0;
+            aphase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;             // TMEM lane quadrant accessible to this warp
+    const int row_in_tile = q * 32 + lane;
+    const int epi_tid = threadIdx.x - (kGemmThreads - kEpiThreads);
+    Epi epi(ep, epi_smem, epi_tid, row_in_tile);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const WorkUnit w = schedule_get(sched, u);
+      for (int n_off = 0; n_off < w.n_rows; n_off += kBN) {
+        TileInfo t;
+        t.m0 = w.m0;
+        t.n0 = w.n0 + n_off;
+        t.n_valid = min(kBN, w.n_rows - n_off);
+        t.unit_index = u;
+        t.first_in_unit = n_off == 0;
+        t.last_in_unit = n_off + kBN >= w.n_rows;
+        epi.tile_begin(t, as);  // may stage per-column metadata (overlaps the MMAs)
+        mbar_wait(&bar_tfull[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(as * kBN);
+        epi.tile_body(t, as, taddr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[as]);
+        epi.tile_end(t, as);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int make_operand_tensor_map(CUtensorMap* map, const __half* base, int rows, int d, int pitch,
+                            int box_rows);
+
+struct GemmOperands {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int num_k_blocks;
+};
+int make_gemm_operands(const PrepView& a, const PrepView& b, GemmOperands* ops);
+
+Schedule make_dense_schedule(int M, int N);
+Schedule make_chunked_schedule(int M, int N, int chunk_tiles);
+Schedule make_list_schedule(int M, int N, const int4* list, const int* list_count);
+
+template <class Epi>
+int launch_sqdist_gemm(const GemmOperands& ops, const Schedule& sched, int max_units,
+                       const typename Epi::Params& ep, cudaStream_t stream) {
+  if (max_units <= 0) return DEMO_OK;
+  auto kernel = sqdist_gemm_kernel<Epi>;
+  constexpr int smem = GemmSmem<Epi>::kTotal;
+  static_assert(smem <= 232448, "shared memory budget exceeded");
+  static bool configured = false;
+  if (!configured) {
+    DEMO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = max_units < num_sms() ? max_units : num_sms();
+  kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo, sched,
+                                               ops.num_k_blocks, ep);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  return DEMO_OK;
+}
+
+}  // namespace demo
