@@ -1,0 +1,303 @@
+// extern "C" entry points for the rank-count evaluation (include/demo_b200.h).
+#include "gemm_epilogues.cuh"
+#include "rank.cuh"
+
+using namespace demo;
+
+namespace {
+
+// Caller-owned evaluation workspace (same carve for sizing and slicing).
+struct EvalWs {
+  PrepView a, b;          // prepared queries / gallery, pid-sorted row order
+  int* b_gidx;            // [G] global gallery index of every sorted gallery row
+  float* rec_dist;        // [T] records (only used by the one-call path)
+  int* rec_gidx;
+  int* rec_junk;
+  int* thr_cnt;           // [Q]
+  float* thr_val;         // [T]
+  int* thr_gidx;
+  int* thr_junk;
+  unsigned* counts;       // [T]
+  double* ap;             // [Q]
+  int* first;             // [Q]
+  double* scratch;        // [4096/2]
+  float* cmc;             // [4096]
+  double* map;            // [1]
+  int* nvalid;            // [1]
+};
+
+size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w) {
+  EvalWs t;
+  const size_t t1 = T > 0 ? static_cast<size_t>(T) : 1, q1 = Q > 0 ? Q : 1, g1 = G > 0 ? G : 1;
+  prep_carve(c, Q, d, &t.a);
+  prep_carve(c, G, d, &t.b);
+  t.b_gidx = c.take<int>(g1);
+  t.rec_dist = c.take<float>(t1);
+  t.rec_gidx = c.take<int>(t1);
+  t.rec_junk = c.take<int>(t1);
+  t.thr_cnt = c.take<int>(q1);
+  t.thr_val = c.take<float>(t1);
+  t.thr_gidx = c.take<int>(t1);
+  t.thr_junk = c.take<int>(t1);
+  t.counts = c.take<unsigned>(t1);
+  t.ap = c.take<double>(q1);
+  t.first = c.take<int>(q1);
+  t.scratch = c.take<double>(2048);
+  t.cmc = c.take<float>(4096);
+  t.map = c.take<double>(1);
+  t.nvalid = c.take<int>(4);
+  if (w) *w = t;
+  return c.off;
+}
+
+__global__ void gidx_kernel(const int* __restrict__ g_perm, int G, int base, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < G) out[i] = base + g_perm[i];
+}
+
+int get_plan(const void* plan, size_t plan_bytes, int Q, int G, PlanView* p) {
+  Carver c(const_cast<void*>(plan), plan_bytes);
+  plan_carve(c, Q, G, p);
+  if (!plan || !c.ok()) {
+    set_error("plan buffer missing or too small (%zu < %zu)", plan_bytes, c.off);
+    return DEMO_ERR_WORKSPACE;
+  }
+  return DEMO_OK;
+}
+
+int get_ws(void* ws, size_t ws_bytes, int Q, int G, int d, long long T, EvalWs* w) {
+  Carver c(ws, ws_bytes);
+  carve_eval(c, Q, G, d, T, w);
+  if (!ws || !c.ok()) {
+    set_error("eval workspace missing or too small (%zu < %zu)", ws_bytes, c.off);
+    return DEMO_ERR_WORKSPACE;
+  }
+  return DEMO_OK;
+}
+
+int norm_mode_of(int flags) {
+  if (flags & DEMO_FLAG_L2NORM) return PREP_NORM_F_NORMALIZE;
+  if (flags & DEMO_FLAG_TRIPLET_NORM) return PREP_NORM_TRIPLET;
+  return PREP_NORM_NONE;
+}
+
+int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int* thr_cnt, const float* thr_val,
+                   const int* thr_gidx, unsigned* counts, int max_cnt, int chunk_tiles, cudaStream_t stream) {
+  GemmOperands ops;
+  DEMO_TRY(make_gemm_operands(w.a, w.b, &ops));
+  EpiCount::Params ep;
+  ep.a_norm = w.a.norm;
+  ep.a_inv = w.a.inv_scale;
+  ep.b_norm = w.b.norm;
+  ep.b_inv = w.b.inv_scale;
+  ep.b_gidx = w.b_gidx;
+  ep.thr_ofs = thr_ofs;
+  ep.thr_cnt = thr_cnt;
+  ep.thr_val = thr_val;
+  ep.thr_gidx = thr_gidx;
+  ep.counts = counts;
+  ep.M = Q;
+  if (chunk_tiles <= 0) {
+    // enough units to balance 148 persistent CTAs (>= ~8 units each) but long enough to
+    // amortise the per-unit threshold load / histogram flush
+    const int n_tiles = ceil_div(G, kBN), m_blocks = ceil_div(Q, kBM);
+    chunk_tiles = 32;
+    while (chunk_tiles > 1 && static_cast<long long>(m_blocks) * ceil_div(n_tiles, chunk_tiles) < 8ll * num_sms())
+      chunk_tiles >>= 1;
+  }
+  const Schedule s = make_chunked_schedule(Q, G, chunk_tiles);
+  const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kWin);
+  for (int wdw = 0; wdw < windows; ++wdw) {
+    ep.window = wdw;
+    DEMO_TRY(launch_sqdist_gemm<EpiCount>(ops, s, s.num_units, ep, stream));
+  }
+  return DEMO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t demo_plan_bytes(int Q, int G) {
+  Carver c(nullptr, ~size_t(0));
+  return round_up(plan_carve(c, Q, G, nullptr), size_t(1024));
+}
+
+int demo_eval_plan(const int* q_pid, const int* g_pid, int Q, int G, void* plan, size_t plan_bytes,
+                   int64_t* info_host, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEMO_REQUIRE(q_pid && g_pid, "eval_plan: null labels");
+  PlanView p;
+  DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
+  DEMO_TRY(run_plan(q_pid, g_pid, p, stream));
+  if (info_host) {
+    int h[4];
+    DEMO_CHECK_CUDA(cudaMemcpyAsync(h, p.info, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    DEMO_CHECK_CUDA(cudaStreamSynchronize(stream));
+    for (int k = 0; k < 4; ++k) info_host[k] = h[k];
+    if (h[2] > p.band_cap) {
+      set_error("eval_plan: band list capacity exceeded (%d > %d)", h[2], p.band_cap);
+      return DEMO_ERR_CAPACITY;
+    }
+  }
+  return DEMO_OK;
+}
+
+int demo_plan_pointers(const void* plan, size_t plan_bytes, int Q, int G, const int** q_perm,
+                       const int** g_perm, const int** rec_ofs, const int** g_lo) {
+  PlanView p;
+  DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
+  if (q_perm) *q_perm = p.q_perm;
+  if (g_perm) *g_perm = p.g_perm;
+  if (rec_ofs) *rec_ofs = p.rec_ofs;
+  if (g_lo) *g_lo = p.g_lo;
+  return DEMO_OK;
+}
+
+size_t demo_eval_workspace_bytes(int Q, int G, int d, int64_t T) {
+  Carver c(nullptr, ~size_t(0));
+  return round_up(carve_eval(c, Q, G, d, T, nullptr), size_t(1024));
+}
+
+size_t demo_eval_matrix_workspace_bytes(int Q, int G, int64_t T) { return demo_eval_workspace_bytes(Q, G, 8, T); }
+
+int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg, int flags,
+                      const int* q_cam, const int* g_cam, int g_index_base, const void* plan,
+                      size_t plan_bytes, int64_t T, void* ws, size_t ws_bytes, float* rec_dist,
+                      int* rec_gidx, int* rec_junk, float* qn_out, float* gn_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEMO_REQUIRE(q && g && q_cam && g_cam, "eval_records: null pointer");
+  DEMO_REQUIRE(Q > 0 && G > 0 && d > 0 && ldq >= d && ldg >= d, "eval_records: bad shape");
+  PlanView p;
+  EvalWs w;
+  DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
+  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T, &w));
+  if (!rec_dist) rec_dist = w.rec_dist;
+  if (!rec_gidx) rec_gidx = w.rec_gidx;
+  if (!rec_junk) rec_junk = w.rec_junk;
+  const int nm = norm_mode_of(flags);
+  DEMO_TRY(launch_prep_rows(q, Q, d, ldq, nm, p.q_perm, w.a, qn_out, d, stream));
+  DEMO_TRY(launch_prep_rows(g, G, d, ldg, nm, p.g_perm, w.b, gn_out, d, stream));
+  gidx_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(p.g_perm, G, g_index_base, w.b_gidx);
+  DEMO_TRY(launch_fill_records(p, q_cam, g_cam, g_index_base, rec_gidx, rec_junk, stream));
+  if (T > 0) {
+    GemmOperands ops;
+    DEMO_TRY(make_gemm_operands(w.a, w.b, &ops));
+    EpiExtract::Params ep;
+    ep.a_norm = w.a.norm;
+    ep.a_inv = w.a.inv_scale;
+    ep.b_norm = w.b.norm;
+    ep.b_inv = w.b.inv_scale;
+    ep.a_pid = p.q_pid_sorted;
+    ep.b_pid = p.g_pid_sorted;
+    ep.g_lo = p.g_lo;
+    ep.rec_base = p.rec_ofs;
+    ep.rec_dist = rec_dist;
+    ep.M = Q;
+    const Schedule s = make_list_schedule(Q, G, p.band_list, p.band_count);
+    DEMO_TRY(launch_sqdist_gemm<EpiExtract>(ops, s, p.band_cap, ep, stream));
+  }
+  return DEMO_OK;
+}
+
+int demo_build_thresholds(const int* rec_ofs, const float* rec_dist, const int* rec_gidx, const int* rec_junk,
+                          int Q, int* thr_cnt, float* thr_val, int* thr_gidx, int* thr_junk, void* stream_) {
+  DEMO_REQUIRE(rec_ofs && thr_cnt, "build_thresholds: null pointer");
+  return launch_build_thresholds(rec_ofs, rec_dist, rec_gidx, rec_junk, Q, thr_cnt, thr_val, thr_gidx, thr_junk,
+                                 static_cast<cudaStream_t>(stream_));
+}
+
+int demo_eval_count(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes, const int* thr_ofs,
+                    const int* thr_cnt, const float* thr_val, const int* thr_gidx, unsigned* counts,
+                    int max_cnt, int chunk_tiles, void* stream_) {
+  EvalWs w;
+  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T_local, &w));
+  return count_features(w, Q, G, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, chunk_tiles,
+                        static_cast<cudaStream_t>(stream_));
+}
+
+int demo_cmc_map_finalize(const int* thr_ofs, const int* thr_cnt, const int* thr_junk, const unsigned* counts,
+                          const int* q_perm, int Q, int max_rank, float* cmc_out, double* map_out,
+                          int* num_valid_out, double* ap_out, int* first_out, void* scratch, void* stream_) {
+  DEMO_REQUIRE(thr_ofs && thr_cnt && thr_junk && counts && q_perm && cmc_out && map_out && num_valid_out &&
+                   ap_out && first_out && scratch,
+               "finalize: null pointer");
+  return launch_finalize(thr_ofs, thr_cnt, thr_junk, counts, q_perm, Q, max_rank, cmc_out, map_out, num_valid_out,
+                         ap_out, first_out, static_cast<double*>(scratch), static_cast<cudaStream_t>(stream_));
+}
+
+// One call, one GPU: features -> (cmc, mAP, num_valid, per-query AP / first rank).
+// Replaces euclidean_distance + eval_func of R1_mAP_eval.compute (utils/metrics.py:341-369)
+// without materialising the Q x G matrix.  Outputs are DEVICE pointers (cmc_out[max_rank]).
+int demo_eval_features(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg, int flags,
+                       const int* q_cam, const int* g_cam, const void* plan, size_t plan_bytes, int64_t T,
+                       int max_cnt, int max_rank, void* ws, size_t ws_bytes, float* cmc_out, double* map_out,
+                       int* num_valid_out, double* ap_out, int* first_out, float* qn_out, float* gn_out,
+                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PlanView p;
+  EvalWs w;
+  DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
+  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T, &w));
+  DEMO_TRY(demo_eval_records(q, g, Q, G, d, ldq, ldg, flags, q_cam, g_cam, 0, plan, plan_bytes, T, ws, ws_bytes,
+                             nullptr, nullptr, nullptr, qn_out, gn_out, stream_));
+  DEMO_TRY(launch_build_thresholds(p.rec_ofs, w.rec_dist, w.rec_gidx, w.rec_junk, Q, w.thr_cnt, w.thr_val,
+                                   w.thr_gidx, w.thr_junk, stream));
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, sizeof(unsigned) * (T > 0 ? T : 1), stream));
+  if (T > 0)
+    DEMO_TRY(count_features(w, Q, G, p.rec_ofs, w.thr_cnt, w.thr_val, w.thr_gidx, w.counts, max_cnt, 0, stream));
+  return launch_finalize(p.rec_ofs, w.thr_cnt, w.thr_junk, w.counts, p.q_perm, Q, max_rank,
+                         cmc_out ? cmc_out : w.cmc, map_out ? map_out : w.map, num_valid_out ? num_valid_out : w.nvalid,
+                         ap_out ? ap_out : w.ap, first_out ? first_out : w.first, w.scratch, stream);
+}
+
+// Materialised matrix: eval_func(distmat, ...) (utils/metrics.py:110-169).  distmat is a DEVICE
+// matrix [Q][G]; the plan must have been built from the same labels.
+int demo_eval_matrix(const float* distmat, int Q, int G, int64_t ld, const int* q_cam, const int* g_cam,
+                     const void* plan, size_t plan_bytes, int64_t T, int max_cnt, int max_rank, void* ws,
+                     size_t ws_bytes, float* cmc_out, double* map_out, int* num_valid_out, double* ap_out,
+                     int* first_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEMO_REQUIRE(distmat && ld >= G, "eval_matrix: bad matrix");
+  PlanView p;
+  EvalWs w;
+  DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
+  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, 8, T, &w));
+  DEMO_TRY(launch_fill_records(p, q_cam, g_cam, 0, w.rec_gidx, w.rec_junk, stream));
+  DEMO_TRY(launch_gather_records(p, distmat, ld, w.rec_dist, stream));
+  DEMO_TRY(launch_build_thresholds(p.rec_ofs, w.rec_dist, w.rec_gidx, w.rec_junk, Q, w.thr_cnt, w.thr_val,
+                                   w.thr_gidx, w.thr_junk, stream));
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, sizeof(unsigned) * (T > 0 ? T : 1), stream));
+  if (T > 0)
+    DEMO_TRY(launch_count_matrix(distmat, ld, G, 0, p.q_perm, p.rec_ofs, w.thr_cnt, w.thr_val, w.thr_gidx, w.counts,
+                                 Q, max_cnt, stream));
+  return launch_finalize(p.rec_ofs, w.thr_cnt, w.thr_junk, w.counts, p.q_perm, Q, max_rank,
+                         cmc_out ? cmc_out : w.cmc, map_out ? map_out : w.map, num_valid_out ? num_valid_out : w.nvalid,
+                         ap_out ? ap_out : w.ap, first_out ? first_out : w.first, w.scratch, stream);
+}
+
+// Device pointers of the result slots inside an eval workspace (for callers that passed NULL
+// outputs to demo_eval_features / demo_eval_matrix) and of the intermediate arrays.
+int demo_eval_ws_pointers(void* ws, size_t ws_bytes, int Q, int G, int d, int64_t T, float** cmc, double** map,
+                          int** nvalid, double** ap, int** first, unsigned** counts, int** thr_cnt,
+                          float** thr_val, int** thr_gidx, int** thr_junk, float** rec_dist, int** rec_gidx,
+                          int** rec_junk) {
+  EvalWs w;
+  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T, &w));
+  if (cmc) *cmc = w.cmc;
+  if (map) *map = w.map;
+  if (nvalid) *nvalid = w.nvalid;
+  if (ap) *ap = w.ap;
+  if (first) *first = w.first;
+  if (counts) *counts = w.counts;
+  if (thr_cnt) *thr_cnt = w.thr_cnt;
+  if (thr_val) *thr_val = w.thr_val;
+  if (thr_gidx) *thr_gidx = w.thr_gidx;
+  if (thr_junk) *thr_junk = w.thr_junk;
+  if (rec_dist) *rec_dist = w.rec_dist;
+  if (rec_gidx) *rec_gidx = w.rec_gidx;
+  if (rec_junk) *rec_junk = w.rec_junk;
+  return DEMO_OK;
+}
+
+}  // extern "C"

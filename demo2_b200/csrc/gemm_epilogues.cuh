@@ -143,7 +143,8 @@ struct EpiCount {
     const float* b_norm;
     const float* b_inv;
     const int* b_gidx;        // global gallery index of every B row (tie-break)
-    const int* thr_ofs;       // [M+1] CSR offsets into thr_val / thr_gidx / counts
+    const int* thr_ofs;       // [M] offsets into thr_val / thr_gidx / counts
+    const int* thr_cnt;       // [M] number of thresholds (valid positives) of the row
     const float* thr_val;     // thresholds, ascending per row
     const int* thr_gidx;      // their global gallery indices
     unsigned* counts;         // += #{gallery columns lexicographically before the threshold}
@@ -168,9 +169,8 @@ struct EpiCount {
       const int row = t.m0 + row_in_tile;
       nthr = 0;
       if (row < p.M) {
-        const int s = __ldg(p.thr_ofs + row), e = __ldg(p.thr_ofs + row + 1);
-        tbase = s + p.window * kWin;
-        nthr = max(0, min(kWin, e - tbase));
+        tbase = __ldg(p.thr_ofs + row) + p.window * kWin;
+        nthr = max(0, min(kWin, __ldg(p.thr_cnt + row) - p.window * kWin));
       }
       for (int k = 0; k < kWin; ++k)
         s_thr[k * kEpiThreads + epi_tid] = k < nthr ? __ldg(p.thr_val + tbase + k) : INFINITY;
@@ -194,9 +194,9 @@ struct EpiCount {
       tmem_ld_wait();
       const int nv = min(32, t.n_valid - c * 32);
       if (!active || nv <= 0) continue;
-#pragma unroll 8
+#pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (j >= nv) break;
+        if (j >= nv) continue;
         const int cc = c * 32 + j;
         const float dot = __uint_as_float(r[j]) * ia * cols.s_binv[as * kBN + cc];
         const float d = fmaf(-2.f, dot, na + cols.s_bnorm[as * kBN + cc]);

@@ -62,7 +62,7 @@ prep_rows_kernel(const float* __restrict__ x, int rows, int d, long long ldx, in
     if (k < d) {
       y = __ldg(xr + k);
       if (do_norm) y = y / denom;
-      if (xn_out) xn_out[static_cast<long long>(r) * ldxn + k] = y;
+      if (xn_out) xn_out[static_cast<long long>(src) * ldxn + k] = y;
     }
     ss2 = fmaf(y, y, ss2);
     const float ys = ldexpf(y, e);

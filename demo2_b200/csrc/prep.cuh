@@ -49,7 +49,7 @@ enum : int {
 };
 
 // perm (optional): output row r is input row perm[r].  xn_out (optional): normalised fp32 rows
-// written in OUTPUT order.
+// written in INPUT order (row perm[r]).
 int launch_prep_rows(const float* x, int rows, int d, long long ldx, int norm_mode,
                      const int* perm, const PrepView& out, float* xn_out, long long ldxn,
                      cudaStream_t stream);

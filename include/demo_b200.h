@@ -64,6 +64,60 @@ DEMO_API int demo_sqdist_f32(const float* q, const float* g, int Q, int G, int d
                              float* qn_out, float* gn_out, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ---- CMC / mAP by rank counts ------------------------------------------------------------
+ * Replaces eval_func (utils/metrics.py:110-169) and the distance + eval part of
+ * R1_mAP_eval.compute (utils/metrics.py:341-369).  For every valid positive p of query q:
+ * r_p = 1 + #{valid g before p}, c_p = 1 + #{positive g before p}, "before" = lexicographic on
+ * (distance, gallery index); AP = mean_p c_p/r_p, CMC[k] = [min_p r_p <= k+1].  The counts are
+ * additive over gallery shards (multi-GPU: all-gather records, all-reduce counts).
+ *
+ * Stages (each an entry point so that a host can put collectives between them):
+ *   demo_eval_plan         labels -> pid-sorted permutations, record CSR, band work list
+ *   demo_eval_records      prepare operands; distances/global index/junk flag of every
+ *                          same-identity (query, gallery) pair  ("records", CSR by sorted query)
+ *   demo_build_thresholds  per query: valid positives sorted by (d, gidx) + #junk before each
+ *   demo_eval_count        += #{local gallery items before each threshold}  (fused GEMM epilogue)
+ *   demo_cmc_map_finalize  counts -> per-query AP / first rank -> cmc[max_rank], mAP, #valid
+ * demo_eval_features chains them on one GPU; demo_eval_matrix does the same for a materialised
+ * distance matrix (one streaming pass, 4 B per pair).                                         */
+DEMO_API size_t demo_plan_bytes(int Q, int G);
+/* info_host (optional, host int64[4]) = {T records, max same-pid count, band units, 0};
+ * when given the call synchronises `stream`. */
+DEMO_API int demo_eval_plan(const int* q_pid, const int* g_pid, int Q, int G, void* plan, size_t plan_bytes,
+                            int64_t* info_host, void* stream);
+DEMO_API int demo_plan_pointers(const void* plan, size_t plan_bytes, int Q, int G, const int** q_perm,
+                                const int** g_perm, const int** rec_ofs, const int** g_lo);
+DEMO_API size_t demo_eval_workspace_bytes(int Q, int G, int d, int64_t T);
+DEMO_API size_t demo_eval_matrix_workspace_bytes(int Q, int G, int64_t T);
+DEMO_API int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg,
+                               int flags, const int* q_cam, const int* g_cam, int g_index_base,
+                               const void* plan, size_t plan_bytes, int64_t T, void* ws, size_t ws_bytes,
+                               float* rec_dist, int* rec_gidx, int* rec_junk, float* qn_out, float* gn_out,
+                               void* stream);
+DEMO_API int demo_build_thresholds(const int* rec_ofs, const float* rec_dist, const int* rec_gidx,
+                                   const int* rec_junk, int Q, int* thr_cnt, float* thr_val, int* thr_gidx,
+                                   int* thr_junk, void* stream);
+DEMO_API int demo_eval_count(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes, const int* thr_ofs,
+                             const int* thr_cnt, const float* thr_val, const int* thr_gidx, unsigned* counts,
+                             int max_cnt, int chunk_tiles, void* stream);
+DEMO_API int demo_cmc_map_finalize(const int* thr_ofs, const int* thr_cnt, const int* thr_junk,
+                                   const unsigned* counts, const int* q_perm, int Q, int max_rank,
+                                   float* cmc_out, double* map_out, int* num_valid_out, double* ap_out,
+                                   int* first_out, void* scratch, void* stream);
+DEMO_API int demo_eval_features(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg,
+                                int flags, const int* q_cam, const int* g_cam, const void* plan,
+                                size_t plan_bytes, int64_t T, int max_cnt, int max_rank, void* ws,
+                                size_t ws_bytes, float* cmc_out, double* map_out, int* num_valid_out,
+                                double* ap_out, int* first_out, float* qn_out, float* gn_out, void* stream);
+DEMO_API int demo_eval_matrix(const float* distmat, int Q, int G, int64_t ld, const int* q_cam, const int* g_cam,
+                              const void* plan, size_t plan_bytes, int64_t T, int max_cnt, int max_rank,
+                              void* ws, size_t ws_bytes, float* cmc_out, double* map_out, int* num_valid_out,
+                              double* ap_out, int* first_out, void* stream);
+DEMO_API int demo_eval_ws_pointers(void* ws, size_t ws_bytes, int Q, int G, int d, int64_t T, float** cmc,
+                                   double** map, int** nvalid, double** ap, int** first, unsigned** counts,
+                                   int** thr_cnt, float** thr_val, int** thr_gidx, int** thr_junk,
+                                   float** rec_dist, int** rec_gidx, int** rec_junk);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,179 @@
+"""GPU parity: distance matrix, eval_func, fused feature evaluation, evaluator -- against the
+CPU oracle and the golden vectors minted from the reference.  All calls go through the C ABI
+(libdemo_b200.so) via the drop-in Python surface."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden, make_case, oracle, sample_index
+
+pytestmark = pytest.mark.gpu
+
+DIST_RTOL, DIST_ATOL = 1e-5, 2e-6   # BASELINE.json: 1e-5 relative (+ absolute floor for ~0 entries)
+XGEMM_METRIC_ATOL = 5e-6            # see tests/test_oracle_golden.py
+
+
+@pytest.fixture(scope="module")
+def M():
+    from demo2_b200 import metrics
+    return metrics
+
+
+def _oracle_per_query(dist, qp, gp, qc, gc):
+    ofs, idx, r, c = oracle.rank_counts(dist, qp, gp, qc, gc)
+    Q = len(ofs) - 1
+    ap = np.full(Q, -1.0)
+    first = np.zeros(Q, np.int64)
+    for q in range(Q):
+        s, e = ofs[q], ofs[q + 1]
+        if e > s:
+            ap[q] = (c[s:e] / r[s:e]).sum() / (e - s)
+            first[q] = r[s:e].min()
+    return ap, first
+
+
+@pytest.mark.parametrize("shape,seed", [("rgbnt201", 0), ("rgbnt201", 1), ("msvr310", 0)])
+def test_distance_matches_oracle_and_golden(M, shape, seed):
+    qf, gf, *_ = make_case(shape, seed, 4.0)
+    ours = M.euclidean_distance(qf, gf)
+    assert ours.dtype == np.float32 and ours.shape == (qf.shape[0], gf.shape[0])
+    ref = oracle.euclidean_distance(qf, gf)
+    np.testing.assert_allclose(ours, ref, rtol=DIST_RTOL, atol=DIST_ATOL)
+    g = load_golden("eval_%s_s%d" % (shape, seed))
+    si = sample_index(*ours.shape)
+    np.testing.assert_allclose(ours.ravel()[si], g["dist_sample"], rtol=DIST_RTOL, atol=DIST_ATOL)
+    # the FFMA cross-check kernel agrees with the tensor-core path
+    simt = M.sqdist_device(qf, gf, simt=True).cpu().numpy()
+    np.testing.assert_allclose(ours, simt, rtol=DIST_RTOL, atol=DIST_ATOL)
+
+
+def test_distance_ragged_shapes_and_modes(M):
+    rng = np.random.default_rng(0)
+    for Q, G, d in [(1, 1, 8), (3, 5, 1), (129, 257, 33), (130, 515, 520), (64, 1000, 1536)]:
+        q = rng.standard_normal((Q, d)).astype(np.float32)
+        g = rng.standard_normal((G, d)).astype(np.float32)
+        np.testing.assert_allclose(M.euclidean_distance(q, g), oracle.euclidean_distance(q, g),
+                                   rtol=1e-5, atol=1e-5 * d)
+        np.testing.assert_allclose(M.cosine_similarity(q, g), oracle.cosine_similarity(q, g), rtol=1e-5, atol=2e-6)
+    # strided input (leading dimension > d) and a cuda tensor input
+    big = torch.randn(50, 300, device="cuda")
+    q, g = big[:20, :100], big[20:, :100]
+    np.testing.assert_allclose(M.euclidean_distance(q, g),
+                               oracle.euclidean_distance(q.cpu().numpy(), g.cpu().numpy()), rtol=1e-5, atol=1e-3)
+
+
+def test_eval_func_exact_on_given_matrix(M):
+    """Same matrix in -> integer rank counts identical to the oracle (bit-exact index work)."""
+    g = load_golden("fullmat_rgbnt201_256x320")
+    _, _, qp, gp, qc, gc = make_case("rgbnt201", 0, 5.0)
+    qp, gp, qc, gc = qp[:256], gp[:320], qc[:256], gc[:320]
+    for key in ("dist", "final_20_6", "final_50_15"):   # plain and tie-heavy (fp16-quantised) matrices
+        dist = g[key]
+        cmc, mAP = M.eval_func(dist, qp, gp, qc, gc)
+        cmc_o, mAP_o = oracle.eval_func(dist, qp, gp, qc, gc)
+        np.testing.assert_allclose(cmc, cmc_o, atol=1e-7)
+        assert abs(mAP - mAP_o) < 1e-12
+        res = M.evaluate_matrix(dist, qp, gp, qc, gc)
+        ap_o, first_o = _oracle_per_query(dist, qp, gp, qc, gc)
+        np.testing.assert_array_equal(res.first.cpu().numpy(), first_o)
+        np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
+    # reference metrics on the reference's own matrix
+    cmc, mAP = M.eval_func(g["dist"], qp, gp, qc, gc)
+    np.testing.assert_allclose(cmc, g["cmc"], atol=1e-7)
+    assert abs(mAP - float(g["mAP"])) < 1e-12
+
+
+def test_eval_func_edge_cases(M):
+    dist = np.array([[1, 3, 2, 4], [4, 1, 2, 3]], np.float32)
+    qp, qc = np.array([7, 8]), np.array([0, 0])
+    gp, gc = np.array([7, 9, 7, 8]), np.array([0, 1, 1, 1])
+    cmc, mAP = M.eval_func(dist, qp, gp, qc, gc, max_rank=3)
+    np.testing.assert_allclose(cmc, [0.5, 0.5, 1.0])
+    assert abs(mAP - (1 + 1 / 3) / 2) < 1e-12
+    cmc, mAP = M.eval_func(dist, qp, gp, np.array([5, 5]), gc, max_rank=50)   # G < max_rank
+    assert cmc.shape == (4,)
+    cmc, mAP = M.eval_func(dist, np.array([7, 5]), gp, qc, gc, max_rank=3)    # identity absent -> skipped
+    np.testing.assert_allclose(cmc, [1, 1, 1])
+    assert mAP == 1.0
+    with pytest.raises(AssertionError):
+        M.eval_func(dist, np.array([5, 5]), gp, qc, gc, max_rank=3)
+    # exact ties -> ascending gallery index
+    res = M.evaluate_matrix(np.array([[1, 1, 1, 1]], np.float32), np.array([1]), np.array([0, 1, 0, 1]),
+                            np.array([0]), np.array([1, 1, 1, 1]), max_rank=4)
+    assert int(res.first[0]) == 2
+    assert abs(float(res.ap[0]) - (1 / 2 + 2 / 4) / 2) < 1e-12
+    # many identical distances + more positives than one threshold window (63)
+    rng = np.random.default_rng(3)
+    dist = rng.integers(0, 7, size=(40, 900)).astype(np.float32)
+    qp, gp = rng.integers(0, 4, 40), rng.integers(0, 4, 900)
+    qc, gc = rng.integers(0, 3, 40), rng.integers(0, 3, 900)
+    res = M.evaluate_matrix(dist, qp, gp, qc, gc)
+    ap_o, first_o = _oracle_per_query(dist, qp, gp, qc, gc)
+    np.testing.assert_array_equal(res.first.cpu().numpy(), first_o)
+    np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape,seed,giq", [("rgbnt201", 0, False), ("rgbnt201", 2, False),
+                                            ("rgbnt201", 0, True), ("msvr310", 0, False),
+                                            ("rgbnt100", 0, False)])
+def test_fused_feature_eval(M, shape, seed, giq):
+    """Fused GEMM-epilogue evaluation == oracle on OUR distance matrix, bit for bit; and within
+    the cross-GEMM tolerance of the reference's golden metrics."""
+    qf, gf, qp, gp, qc, gc = make_case(shape, seed, 4.0, giq)
+    res = M.evaluate_features(qf, gf, qp, gp, qc, gc)
+    ours = M.euclidean_distance(qf, gf)
+    ap_o, first_o = _oracle_per_query(ours, qp, gp, qc, gc)
+    np.testing.assert_array_equal(res.first.cpu().numpy(), first_o)
+    np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
+    cmc_o, mAP_o = oracle.eval_func(ours, qp, gp, qc, gc)
+    np.testing.assert_allclose(res.cmc, cmc_o, atol=1e-7)
+    assert abs(res.mAP - mAP_o) < 1e-12
+    g = load_golden("eval_%s_s%d%s" % (shape, seed, "_giq" if giq else ""))
+    assert abs(res.mAP - float(g["mAP"])) < XGEMM_METRIC_ATOL
+    np.testing.assert_allclose(res.cmc, g["cmc"], atol=2.5 / len(qp))
+    assert (res.first.cpu().numpy() != g["first"]).mean() < 0.01
+
+
+def test_fused_eval_duplicates_and_absent_ids(M):
+    """Exact duplicate rows (bit-ties across identities), an identity absent from the gallery,
+    and un-normalised features with normalize=True."""
+    qf, gf, qp, gp, qc, gc = make_case("rgbnt201", 1, 4.0)
+    qf, gf, qp, gp, qc, gc = qf[:300].copy(), gf[:500].copy(), qp[:300].copy(), gp[:500].copy(), qc[:300], gc[:500]
+    gf[100:200] = gf[:100]          # duplicates with (mostly) different labels
+    gf[250] = qf[7]
+    qp[5] = 12345                   # not in the gallery -> skipped
+    res = M.evaluate_features(qf * 3.0, gf * 0.5, qp, gp, qc, gc, normalize=True, want_normalized=True)
+    qn, gn = res.qn.cpu().numpy(), res.gn.cpu().numpy()
+    np.testing.assert_allclose(qn, oracle.l2_normalize(qf * 3.0), rtol=1e-6, atol=1e-8)
+    ours = M.sqdist_device(qf * 3.0, gf * 0.5, normalize=True).cpu().numpy()
+    ap_o, first_o = _oracle_per_query(ours, qp, gp, qc, gc)
+    np.testing.assert_array_equal(res.first.cpu().numpy(), first_o)
+    np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
+    assert int(res.first[5]) == 0 and float(res.ap[5]) == -1.0
+    assert res.num_valid == int((first_o > 0).sum())
+
+
+def test_evaluator_drop_in(M):
+    from demo2_b200 import synth
+    g = load_golden("evaluator_rgbnt201_s0_sigma5")
+    s = synth.make_named("rgbnt201", sigma=5.0, seed=0)
+    feats = torch.cat([s.qf, s.gf])
+    pids = np.concatenate([s.q_pids, s.g_pids])
+    cams = np.concatenate([s.q_camids, s.g_camids])
+    ev = M.R1_mAP_eval(s.num_query, max_rank=50, feat_norm=True)
+    for b in range(0, feats.shape[0], 128):
+        fb = feats[b:b + 128]
+        if (b // 128) % 2:
+            fb = fb.cuda()          # mixed host / device batches
+        ev.update((fb, tuple(int(p) for p in pids[b:b + 128]), torch.from_numpy(cams[b:b + 128]),
+                   ["x"] * len(pids[b:b + 128])))
+    cmc, mAP, distmat, rpids, rcams, qf, gf = ev.compute()
+    assert cmc.dtype == np.float32 and cmc.shape == (50,)
+    assert isinstance(distmat, np.ndarray) and distmat.shape == (836, 836)
+    assert len(rpids) == 1672 and qf.shape == (836, 1536)
+    assert abs(mAP - float(g["plain_mAP"])) < XGEMM_METRIC_ATOL
+    np.testing.assert_allclose(cmc, g["plain_cmc"], atol=2.5 / 836)
+    si = sample_index(*distmat.shape)
+    np.testing.assert_allclose(distmat.ravel()[si], g["plain_dist_sample"], rtol=DIST_RTOL, atol=DIST_ATOL)
