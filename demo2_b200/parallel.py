@@ -1,0 +1,196 @@
+"""Gallery-sharded evaluation: one process per GPU, gallery rows split contiguously over the
+ranks, queries replicated.
+
+Rank counts are sums over gallery items, hence additive over any gallery partition:
+
+    every rank   plan (labels) -> records of its local same-identity pairs      [tcgen05 extract GEMM]
+    all ranks    all-gather the records (KB..MB) and merge them per query       [torch.distributed]
+    every rank   thresholds of the merged records; counts of its LOCAL gallery  [tcgen05 count GEMM]
+    all ranks    all-reduce(sum) of the counts                                  [torch.distributed]
+    every rank   finalize -> identical CMC / mAP on all ranks
+
+The collectives move a few MB once per evaluation, so they are issued through
+torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests); the compute stages are the
+C-ABI entry points of libdemo_b200.  The record merge is plain index arithmetic on tensors and
+runs on whatever device the engine produces (this is what the world_size-2 gloo tests cover,
+with a numpy engine standing in for the CUDA stages).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def shard_range(G: int, world: int, rank: int):
+    """Contiguous gallery shard [lo, hi) of `rank`."""
+    base, rem = divmod(G, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def merge_records(cnt_all: torch.Tensor, recs_all: torch.Tensor):
+    """cnt_all [P, Q] records per (rank, sorted query); recs_all [P, 3, Tmax] int32 rows
+    (dist bits, gidx, junk) in each rank's local CSR order.  Returns the merged CSR offsets
+    [Q+1] (int32) and the merged [3, T_total] records: per query, rank 0's records first."""
+    P, Q = cnt_all.shape
+    cnt_all = cnt_all.to(torch.int64)
+    total = cnt_all.sum(0)
+    ofs = torch.zeros(Q + 1, dtype=torch.int64, device=cnt_all.device)
+    ofs[1:] = torch.cumsum(total, 0)
+    T = int(ofs[-1])
+    merged = torch.zeros((3, max(T, 1)), dtype=torch.int32, device=recs_all.device)
+    rank_prefix = torch.cumsum(cnt_all, 0) - cnt_all
+    qidx_all = torch.arange(Q, device=cnt_all.device)
+    for r in range(P):
+        cnt = cnt_all[r]
+        t_r = int(cnt.sum())
+        if t_r == 0:
+            continue
+        local_ofs = torch.cumsum(cnt, 0) - cnt
+        qidx = torch.repeat_interleave(qidx_all, cnt)
+        within = torch.arange(t_r, device=cnt.device) - local_ofs[qidx]
+        dest = ofs[:-1][qidx] + rank_prefix[r][qidx] + within
+        merged[:, dest] = recs_all[r, :, :t_r]
+    return ofs.to(torch.int32), merged, T, int(total.max()) if Q else 0
+
+
+class CudaEngine:
+    """The compute stages on one GPU (C ABI of libdemo_b200)."""
+
+    def __init__(self):
+        self.lib = _lib.require_device()
+
+    def plan(self, q_pid, g_pid, q_cam, g_cam):
+        from .metrics import RankPlan
+        return RankPlan(q_pid, g_pid, q_cam, g_cam)
+
+    def records(self, plan, qf, gf, g_index_base, normalize):
+        from .metrics import _EvalWorkspace, _features
+        q, g = _features(qf), _features(gf)
+        Q, d = q.shape
+        G = g.shape[0]
+        w = _EvalWorkspace(Q, G, d, plan.T, matrix=False)
+        flags = _lib.FLAG_L2NORM if normalize else 0
+        check(self.lib.demo_eval_records(ptr(q), ptr(g), Q, G, d, q.stride(0), g.stride(0), flags,
+                                         ptr(plan.q_cam), ptr(plan.g_cam), int(g_index_base), ptr(plan.buf),
+                                         plan.nbytes, plan.T, ptr(w.buf), w.nbytes, None, None, None, None, None,
+                                         stream_ptr()))
+        n = max(plan.T, 1)
+        recs = torch.stack([w.view("rec_dist", torch.float32, n).view(torch.int32),
+                            w.view("rec_gidx", torch.int32, n), w.view("rec_junk", torch.int32, n)])
+        return w, recs[:, :plan.T]
+
+    def thresholds(self, rec_ofs, recs, Q):
+        T = recs.shape[1]
+        dev = recs.device
+        n = max(T, 1)
+        thr_cnt = torch.empty(Q, dtype=torch.int32, device=dev)
+        thr_val = torch.empty(n, dtype=torch.float32, device=dev)
+        thr_gidx = torch.empty(n, dtype=torch.int32, device=dev)
+        thr_junk = torch.empty(n, dtype=torch.int32, device=dev)
+        recs = recs.contiguous()
+        check(self.lib.demo_build_thresholds(ptr(rec_ofs), ptr(recs[0]), ptr(recs[1]), ptr(recs[2]), Q,
+                                             ptr(thr_cnt), ptr(thr_val), ptr(thr_gidx), ptr(thr_junk), stream_ptr()))
+        return thr_cnt, thr_val, thr_gidx, thr_junk
+
+    def count(self, w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt):
+        check(self.lib.demo_eval_count(w.Q, w.G, w.d, plan.T, ptr(w.buf), w.nbytes, ptr(thr_ofs), ptr(thr_cnt),
+                                       ptr(thr_val), ptr(thr_gidx), ptr(counts), int(max_cnt), 0, stream_ptr()))
+
+    def finalize(self, thr_ofs, thr_cnt, thr_junk, counts, q_perm, Q, max_rank):
+        dev = counts.device
+        cmc = torch.empty(max_rank, dtype=torch.float32, device=dev)
+        scal = torch.empty(4, dtype=torch.float64, device=dev)  # [mAP, nvalid(int bits), -, -]
+        ap = torch.empty(Q, dtype=torch.float64, device=dev)
+        first = torch.empty(Q, dtype=torch.int32, device=dev)
+        scratch = torch.empty(4096, dtype=torch.float64, device=dev)
+        nvalid = scal[1:2].view(torch.int32)
+        check(self.lib.demo_cmc_map_finalize(ptr(thr_ofs), ptr(thr_cnt), ptr(thr_junk), ptr(counts), ptr(q_perm), Q,
+                                             max_rank, ptr(cmc), ptr(scal), ptr(nvalid), ptr(ap), ptr(first),
+                                             ptr(scratch), stream_ptr()))
+        return cmc, scal, ap, first
+
+    def launches(self, windows):
+        # iota, ranges, band list | 2x prep, gidx, fill records, extract GEMM | thresholds |
+        # count GEMM x windows | per-query AP, reduce   (CUB sort/scan kernels not counted)
+        return 3 + 5 + 1 + windows + 2
+
+    @staticmethod
+    def event():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+
+class ShardedEvaluator:
+    def __init__(self, world: int = 1, rank: int = 0, group=None, engine=None):
+        self.world, self.rank, self.group = world, rank, group
+        self.engine = engine if engine is not None else CudaEngine()
+
+    # -- collectives (torch.distributed; NCCL on GPUs, gloo in the CPU tests) --
+    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        flat = t.contiguous().view(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.view((self.world,) + tuple(t.shape))
+
+    def _all_reduce_sum(self, t: torch.Tensor):
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def evaluate(self, qf, gf_local, q_pid, g_pid_local, q_cam, g_cam_local, g_index_base: int = 0,
+                 normalize: bool = False, max_rank: int = 50, timers: dict | None = None):
+        from .metrics import EvalResult
+        eng = self.engine
+        ev = getattr(eng, "event", None) if timers is not None else None
+        mark = (lambda: ev()) if ev else (lambda: None)
+
+        t0 = mark()
+        plan = eng.plan(q_pid, g_pid_local, q_cam, g_cam_local)
+        Q = plan.Q
+        t1 = mark()
+        w, recs = eng.records(plan, qf, gf_local, g_index_base, normalize)
+        t2 = mark()
+        if self.world > 1:
+            cnt_local = (plan.rec_ofs[1:] - plan.rec_ofs[:-1]).to(torch.int32)
+            sizes = self._all_gather(torch.tensor([plan.T], dtype=torch.int64, device=cnt_local.device))
+            t_max = int(sizes.max())
+            cnt_all = self._all_gather(cnt_local)
+            padded = torch.zeros((3, max(t_max, 1)), dtype=torch.int32, device=recs.device)
+            padded[:, :plan.T] = recs
+            recs_all = self._all_gather(padded)
+            thr_ofs, merged, T, max_cnt = merge_records(cnt_all, recs_all)
+        else:
+            thr_ofs, merged, T, max_cnt = plan.rec_ofs, recs, plan.T, plan.max_cnt
+        t3 = mark()
+        thr_cnt, thr_val, thr_gidx, thr_junk = eng.thresholds(thr_ofs, merged, Q)
+        counts = torch.zeros(max(T, 1), dtype=torch.int32, device=merged.device)
+        t4 = mark()
+        if T > 0:
+            eng.count(w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt)
+        t5 = mark()
+        if self.world > 1:
+            self._all_reduce_sum(counts)
+        t6 = mark()
+        G_total = plan.G
+        if self.world > 1:
+            G_total = int(self._all_gather(torch.tensor([plan.G], dtype=torch.int64, device=counts.device)).sum())
+        if G_total < max_rank:
+            max_rank = G_total
+        cmc_d, scal_d, ap, first = eng.finalize(thr_ofs, thr_cnt, thr_junk, counts, plan.q_perm, Q, max_rank)
+        cmc = cmc_d.cpu().numpy()
+        scal = scal_d.cpu()
+        mAP = np.float64(scal[0].item())
+        nvalid = int(scal[1:2].view(torch.int32)[0].item())
+        t7 = mark()
+        if timers is not None and ev:
+            timers.update({"plan": (t0, t1), "records": (t1, t2), "exchange": (t2, t3), "thresholds": (t3, t4),
+                           "count": (t4, t5), "allreduce": (t5, t6), "finalize": (t6, t7)})
+            timers["launches"] = eng.launches(max(1, -(-max_cnt // 63)))
+        return EvalResult(cmc, mAP, nvalid, ap, first)

@@ -1,0 +1,180 @@
+"""World-size-2 (and 3) gloo tests of the gallery-sharded evaluation host logic on CPU.
+
+The CUDA stages are replaced by a numpy engine built on the oracle (test infrastructure);
+what is under test is demo2_b200.parallel: shard ranges, the all-gather / merge of per-rank
+records, threshold CSR handling, the all-reduce of counts and the finalisation flow."""
+from __future__ import annotations
+
+import os
+import socket
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.helpers import make_case, oracle
+
+from demo2_b200 import parallel
+
+
+class NumpyEngine:
+    """Same stage interface as parallel.CudaEngine, computed with numpy on the host."""
+
+    def plan(self, q_pid, g_pid, q_cam, g_cam):
+        q_pid, g_pid = np.asarray(q_pid), np.asarray(g_pid)
+        q_perm = np.argsort(q_pid, kind="stable")
+        g_perm = np.argsort(g_pid, kind="stable")
+        gs = g_pid[g_perm]
+        lo = np.searchsorted(gs, q_pid[q_perm], "left")
+        hi = np.searchsorted(gs, q_pid[q_perm], "right")
+        cnt = hi - lo
+        rec_ofs = np.concatenate([[0], np.cumsum(cnt)])
+        return SimpleNamespace(Q=len(q_pid), G=len(g_pid), T=int(rec_ofs[-1]), max_cnt=int(cnt.max()),
+                               q_perm=torch.from_numpy(q_perm.astype(np.int32)), g_perm=g_perm, g_lo=lo,
+                               rec_ofs=torch.from_numpy(rec_ofs.astype(np.int32)),
+                               q_cam=np.asarray(q_cam), g_cam=np.asarray(g_cam))
+
+    def records(self, plan, qf, gf, g_index_base, normalize):
+        qf, gf = np.asarray(qf, np.float32), np.asarray(gf, np.float32)
+        if normalize:
+            qf, gf = oracle.l2_normalize(qf), oracle.l2_normalize(gf)
+        distmat = oracle.euclidean_distance(qf, gf)
+        recs = np.zeros((3, plan.T), np.int32)
+        ofs = plan.rec_ofs.numpy()
+        for i in range(plan.Q):
+            q = plan.q_perm[i].item()
+            n = ofs[i + 1] - ofs[i]
+            cols = plan.g_perm[plan.g_lo[i]:plan.g_lo[i] + n]
+            recs[0, ofs[i]:ofs[i + 1]] = distmat[q, cols].view(np.int32)
+            recs[1, ofs[i]:ofs[i + 1]] = g_index_base + cols
+            recs[2, ofs[i]:ofs[i + 1]] = plan.g_cam[cols] == plan.q_cam[q]
+        return SimpleNamespace(distmat=distmat, base=g_index_base), torch.from_numpy(recs)
+
+    def thresholds(self, rec_ofs, recs, Q):
+        ofs, recs = rec_ofs.numpy(), recs.numpy()
+        T = recs.shape[1]
+        thr_cnt = np.zeros(Q, np.int32)
+        thr_val = np.zeros(max(T, 1), np.float32)
+        thr_gidx = np.zeros(max(T, 1), np.int32)
+        thr_junk = np.zeros(max(T, 1), np.int32)
+        for i in range(Q):
+            s, e = ofs[i], ofs[i + 1]
+            d, g, j = recs[0, s:e].view(np.float32), recs[1, s:e], recs[2, s:e]
+            order = np.lexsort((g, d))
+            junk_before = np.cumsum(j[order]) - j[order]
+            keep = order[j[order] == 0]
+            n = len(keep)
+            thr_cnt[i] = n
+            thr_val[s:s + n], thr_gidx[s:s + n] = d[keep], g[keep]
+            thr_junk[s:s + n] = junk_before[j[order] == 0]
+        return tuple(torch.from_numpy(a) for a in (thr_cnt, thr_val, thr_gidx, thr_junk))
+
+    def count(self, w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt):
+        ofs, cnt = thr_ofs.numpy(), thr_cnt.numpy()
+        tv, tg, out = thr_val.numpy(), thr_gidx.numpy(), counts.numpy()
+        G = w.distmat.shape[1]
+        gidx = w.base + np.arange(G)
+        for i in range(plan.Q):
+            row = w.distmat[plan.q_perm[i].item()]
+            for k in range(cnt[i]):
+                t, p = tv[ofs[i] + k], tg[ofs[i] + k]
+                out[ofs[i] + k] += int(np.sum((row < t) | ((row == t) & (gidx < p))))
+
+    def finalize(self, thr_ofs, thr_cnt, thr_junk, counts, q_perm, Q, max_rank):
+        ofs, cnt, junk, c = thr_ofs.numpy(), thr_cnt.numpy(), thr_junk.numpy(), counts.numpy()
+        ap = np.full(Q, -1.0)
+        first = np.zeros(Q, np.int32)
+        for i in range(Q):
+            n = cnt[i]
+            if n == 0:
+                continue
+            r = 1 + c[ofs[i]:ofs[i] + n] - junk[ofs[i]:ofs[i] + n]
+            q = q_perm[i].item()
+            ap[q] = np.sum(np.arange(1, n + 1) / r) / n
+            first[q] = r[0]
+        valid = first > 0
+        nv = int(valid.sum())
+        cmc = np.array([(first[valid] <= k + 1).sum() for k in range(max_rank)], np.float32) / np.float32(max(nv, 1))
+        scal = torch.zeros(4, dtype=torch.float64)
+        scal[0] = ap[valid].mean() if nv else 0.0
+        scal[1:2].view(torch.int32)[0] = nv
+        return torch.from_numpy(cmc), scal, torch.from_numpy(ap), torch.from_numpy(first)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        qf, gf, qp, gp, qc, gc = case
+        lo, hi = parallel.shard_range(len(gp), world, rank)
+        ev = parallel.ShardedEvaluator(world=world, rank=rank, group=dist.group.WORLD, engine=NumpyEngine())
+        res = ev.evaluate(qf, gf[lo:hi], qp, gp[lo:hi], qc, gc[lo:hi], g_index_base=lo, max_rank=50)
+        out[rank] = (res.cmc, float(res.mAP), res.num_valid, res.ap.numpy(), res.first.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _small_case():
+    qf, gf, qp, gp, qc, gc = make_case("rgbnt201", 0, 4.0)
+    qf, gf, qp, gp, qc, gc = qf[:60, :128].copy(), gf[:157, :128].copy(), qp[:60].copy(), gp[:157].copy(), qc[:60], gc[:157]
+    gf[40:50] = gf[100:110]      # exact ties across shards
+    qp[3] = 999                  # identity absent -> skipped
+    return qf, gf, qp, gp, qc, gc
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_eval_matches_single_process(world):
+    case = _small_case()
+    qf, gf, qp, gp, qc, gc = case
+    dist_full = oracle.euclidean_distance(qf, gf)
+    cmc_o, mAP_o = oracle.eval_func(dist_full, qp, gp, qc, gc)
+    ofs_o = oracle.rank_counts(dist_full, qp, gp, qc, gc)[0]
+    nv_o = int((np.diff(ofs_o) > 0).sum())
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, case, out), nprocs=world, join=True)
+    assert len(out) == world
+    for r in range(world):
+        cmc, mAP, nv, ap, first = out[r]
+        np.testing.assert_allclose(cmc, cmc_o, atol=1e-7)
+        assert abs(mAP - mAP_o) < 1e-12
+        assert nv == nv_o and first[3] == 0
+    # identical on every rank (bitwise)
+    for r in range(1, world):
+        np.testing.assert_array_equal(out[0][3], out[r][3])
+        np.testing.assert_array_equal(out[0][4], out[r][4])
+
+
+def test_single_rank_flow_and_shard_ranges():
+    for G, world in [(10, 3), (8575, 8), (5, 8), (1000000, 8)]:
+        spans = [parallel.shard_range(G, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == G
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    qf, gf, qp, gp, qc, gc = _small_case()
+    ev = parallel.ShardedEvaluator(engine=NumpyEngine())
+    res = ev.evaluate(qf, gf, qp, gp, qc, gc)
+    cmc_o, mAP_o = oracle.eval_func(oracle.euclidean_distance(qf, gf), qp, gp, qc, gc)
+    np.testing.assert_allclose(res.cmc, cmc_o, atol=1e-7)
+    assert abs(res.mAP - mAP_o) < 1e-12
+
+
+def test_merge_records_layout():
+    cnt = torch.tensor([[2, 0, 1], [1, 3, 0]], dtype=torch.int32)
+    recs = torch.zeros((2, 3, 4), dtype=torch.int32)
+    recs[0, 1, :3] = torch.tensor([10, 11, 12])
+    recs[1, 1, :4] = torch.tensor([20, 21, 22, 23])
+    ofs, merged, T, max_cnt = parallel.merge_records(cnt, recs)
+    assert ofs.tolist() == [0, 3, 6, 7] and T == 7 and max_cnt == 3
+    assert merged[1].tolist() == [10, 11, 20, 21, 22, 23, 12]
