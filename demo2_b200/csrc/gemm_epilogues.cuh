@@ -1,9 +1,10 @@
 // Epilogue policies for sqdist_gemm_kernel.  Each epilogue thread owns ONE accumulator row
-// (one query) and walks the 256 columns of the tile in chunks of 32 TMEM columns; per-column
-// metadata (|g|^2, 2^-e, labels) is staged once per tile in shared memory and read as
-// warp-wide broadcasts.
+// (one query) and one half (128 columns) of the 256-column tile, which it walks in steps of 16
+// or 32 TMEM columns; per-column metadata (|g|^2, 2^-e, labels) is staged once per tile in
+// shared memory and read as warp-wide broadcasts.
 //
-//   dist = fma(-2, acc * ia[m] * ib[n], na[m] + nb[n])     (utils/metrics.py:398-400 order)
+//   dist = fma(acc * 2^-ea[m], -2 * 2^-eb[n], |a_m|^2 + |b_n|^2)
+//        = fma(-2, dot, |a|^2 + |b|^2)  exactly (power-of-two scalings)   utils/metrics.py:398-400
 #pragma once
 
 #include "gemm_sm100.cuh"
@@ -29,25 +30,24 @@ __device__ __forceinline__ float finish_distance(int mode, float dot, float na, 
   return mode == DIST_COS_SIM ? c : (1.f - c) * 0.5f;
 }
 
-// Common base: stages b_norm / b_inv (and optionally an int label) for the tile's columns.
+// Per-tile column metadata: {-2 * 2^-eb[n], |b_n|^2} (+ optional int label), double-buffered.
+// Invalid (out-of-range) columns carry |b|^2 = +inf so their distance is +inf.
 struct EpiColumns {
-  float* s_bnorm;  // [2][kBN]
-  float* s_binv;   // [2][kBN]
-  int* s_blab;     // [2][kBN] (optional)
-  static constexpr int kBytes = 2 * kBN * 4 * 3;
+  float2* s_col;   // [2][kBN]
+  int* s_lab;      // [2][kBN]
+  static constexpr int kBytes = 2 * kBN * 8 + 2 * kBN * 4;
 
   __device__ EpiColumns(uint8_t* smem) {
-    s_bnorm = reinterpret_cast<float*>(smem);
-    s_binv = s_bnorm + 2 * kBN;
-    s_blab = reinterpret_cast<int*>(s_binv + 2 * kBN);
+    s_col = reinterpret_cast<float2*>(smem);
+    s_lab = reinterpret_cast<int*>(smem + 2 * kBN * 8);
   }
   __device__ __forceinline__ void stage(const TileInfo& t, int as, int epi_tid, const float* b_norm,
                                         const float* b_inv, const int* b_lab) {
     for (int c = epi_tid; c < kBN; c += kEpiThreads) {
       const bool ok = c < t.n_valid;
-      s_bnorm[as * kBN + c] = ok ? __ldg(b_norm + t.n0 + c) : 0.f;
-      s_binv[as * kBN + c] = ok ? __ldg(b_inv + t.n0 + c) : 0.f;
-      if (b_lab) s_blab[as * kBN + c] = ok ? __ldg(b_lab + t.n0 + c) : -0x7fffffff;
+      s_col[as * kBN + c] = make_float2(ok ? -2.f * __ldg(b_inv + t.n0 + c) : 0.f,
+                                        ok ? __ldg(b_norm + t.n0 + c) : INFINITY);
+      if (b_lab) s_lab[as * kBN + c] = ok ? __ldg(b_lab + t.n0 + c) : -0x7fffffff;
     }
     epi_bar_sync();
   }
@@ -72,10 +72,10 @@ struct EpiStore {
   };
   const Params& p;
   EpiColumns cols;
-  int epi_tid, row_in_tile;
+  int epi_tid, row_in_tile, col0;
 
-  __device__ EpiStore(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_)
-      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_) {}
+  __device__ EpiStore(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
+      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {}
 
   __device__ void tile_begin(const TileInfo& t, int as) {
     cols.stage(t, as, epi_tid, p.b_norm, p.b_inv, nullptr);
@@ -85,24 +85,31 @@ struct EpiStore {
     const bool row_ok = row < p.M;
     const float na = row_ok ? __ldg(p.a_norm + row) : 0.f;
     const float ia = row_ok ? __ldg(p.a_inv + row) : 0.f;
-    float* orow = p.out + static_cast<long long>(row) * p.ldo + t.n0;
+    float* orow = p.out + static_cast<long long>(row) * p.ldo + t.n0 + col0;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0);
+    const float2* col = cols.s_col + as * kBN + col0;
+    const int n_here = t.n_valid - col0;  // valid columns in this thread's half
     float vmax = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int c = 0; c < kEpiCols / 32; ++c) {
+      if (c * 32 >= n_here) break;  // warp-uniform
       uint32_t r[32];
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-row branches
       tmem_ld_32x32(taddr + c * 32, r);
       tmem_ld_wait();
-      if (!row_ok || c * 32 >= t.n_valid) continue;
+      if (!row_ok) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int cc = c * 32 + j;
-        const float dot = __uint_as_float(r[j]) * ia * cols.s_binv[as * kBN + cc];
-        v[j] = finish_distance(p.mode, dot, na, cols.s_bnorm[as * kBN + cc]);
+        const float2 cm = col[c * 32 + j];
+        if (p.mode == DIST_SQ) {
+          v[j] = fmaf(__uint_as_float(r[j]) * ia, cm.x, na + cm.y);
+        } else {
+          const float dot = __uint_as_float(r[j]) * ia * cm.x * -0.5f;
+          v[j] = finish_distance(p.mode, dot, na, cm.y);
+        }
       }
-      const int nv = min(32, t.n_valid - c * 32);
+      const int nv = min(32, n_here - c * 32);
       if (nv == 32 && vec_ok) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -125,18 +132,33 @@ struct EpiStore {
 
 // ---------------------------------------------------------------------------------------
 // COUNT: rank counts without materialising Q x G.
-// For its row q the thread holds up to kWin thresholds (the distances of q's valid positives,
-// sorted ascending by (distance, gallery index)) in a private shared-memory column and, for
-// every gallery column g, finds   b = #{ j : (t_j, p_j) <=lex (d(q,g), g) }   by binary search
-// and bumps hist[b].  At the end of the unit  #{g before threshold j} = sum_{b<=j} hist[b]
-// is added to counts[].  No labels are read here: junk / positives are subtracted later from
-// the per-query record list (they all belong to it).
+// A row q keeps up to kWin thresholds (the distances of q's valid positives, ascending by
+// (distance, gallery index)) in a shared-memory column; for every gallery column g the thread
+// finds   b = #{ j : (t_j, p_j) <=lex (d(q,g), g) }   by bisection (top three tree levels in
+// registers) and bumps its private 16-bit histogram bucket b.  At the end of the unit
+// #{g before threshold j} = sum_{b<=j} hist[b]  is added to counts[].  No labels are read:
+// junk / positives are subtracted later from the per-query record list.
 // ---------------------------------------------------------------------------------------
 constexpr int kWin = 63;
 
+template <int kOff>
+__device__ __forceinline__ float lds_f32_off(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(kOff));  // not volatile: free to schedule
+  return v;
+}
+__device__ __forceinline__ void hist_inc_u16(uint32_t addr) {  // ordered read-modify-write
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  v += 1u;
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v));
+}
+
 struct EpiCount {
   static constexpr int kStages = 3;
-  static constexpr int kSmemBytes = EpiColumns::kBytes + kWin * kEpiThreads * 4 + (kWin + 1) * kEpiThreads * 4;
+  static constexpr int kRowBytes = 512;  // one bucket row: 128 x f32 thresholds == 256 x u16 counters
+  // columns x2 buffers | thresholds [kWin][128] f32 | histogram [kWin+1][256] u16
+  static constexpr int kSmemBytes = 2 * kBN * 8 + kWin * kRowBytes + (kWin + 1) * kRowBytes;
   struct Params {
     const float* a_norm;
     const float* a_inv;
@@ -152,65 +174,134 @@ struct EpiCount {
     int window;               // thresholds [window*kWin, window*kWin + kWin) of every row
   };
   const Params& p;
-  EpiColumns cols;
-  float* s_thr;   // [kWin][kEpiThreads]   thread-private column = epi_tid
-  unsigned* s_hist;  // [kWin+1][kEpiThreads]
-  int epi_tid, row_in_tile;
+  float2* s_col;              // [2][kBN]
+  float* s_thr;               // [kWin][128]     column = row_in_tile (shared by both column halves)
+  unsigned short* s_hist;     // [kWin+1][256]   column = epi_tid (private)
+  int epi_tid, row_in_tile, col0;
+  int hcol;                   // histogram column: warps 2m / 2m+1 share 32-bit words (low / high half) so
+                              // that the 32 lanes of one warp hit 32 different banks
   int nthr = 0, tbase = 0;
+  // top three levels of the search tree live in registers
+  float t31 = 0, t15 = 0, t47 = 0, t7 = 0, t23 = 0, t39 = 0, t55 = 0;
 
-  __device__ EpiCount(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_)
-      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_) {
-    s_thr = reinterpret_cast<float*>(smem + EpiColumns::kBytes);
-    s_hist = reinterpret_cast<unsigned*>(s_thr + kWin * kEpiThreads);
+  __device__ EpiCount(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
+      : p(p_), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {
+    s_col = reinterpret_cast<float2*>(smem);
+    s_thr = reinterpret_cast<float*>(smem + 2 * kBN * 8);
+    s_hist = reinterpret_cast<unsigned short*>(smem + 2 * kBN * 8 + kWin * kRowBytes);
+    hcol = (((epi_tid >> 6) * 32 + (epi_tid & 31)) << 1) | ((epi_tid >> 5) & 1);
   }
 
   __device__ void tile_begin(const TileInfo& t, int as) {
     if (t.first_in_unit) {
+      // s_thr is shared by the two warps of a lane quadrant: the partner may still be searching
+      // the previous unit's thresholds, so everybody must have left that tile body first
+      epi_bar_sync();
       const int row = t.m0 + row_in_tile;
       nthr = 0;
       if (row < p.M) {
         tbase = __ldg(p.thr_ofs + row) + p.window * kWin;
         nthr = max(0, min(kWin, __ldg(p.thr_cnt + row) - p.window * kWin));
       }
-      for (int k = 0; k < kWin; ++k)
-        s_thr[k * kEpiThreads + epi_tid] = k < nthr ? __ldg(p.thr_val + tbase + k) : INFINITY;
-      for (int k = 0; k <= kWin; ++k) s_hist[k * kEpiThreads + epi_tid] = 0u;
+      // the two threads of a row (column halves) fill alternate threshold slots
+      for (int k = (col0 ? 1 : 0); k < kWin; k += 2)
+        s_thr[k * 128 + row_in_tile] = k < nthr ? __ldg(p.thr_val + tbase + k) : INFINITY;
+      for (int k = 0; k <= kWin; ++k) s_hist[k * kEpiThreads + hcol] = 0;
     }
-    cols.stage(t, as, epi_tid, p.b_norm, p.b_inv, nullptr);
+    for (int c = epi_tid; c < kBN; c += kEpiThreads) {
+      const bool ok = c < t.n_valid;
+      s_col[as * kBN + c] = make_float2(ok ? -2.f * __ldg(p.b_inv + t.n0 + c) : 0.f,
+                                        ok ? __ldg(p.b_norm + t.n0 + c) : INFINITY);
+    }
+    epi_bar_sync();
+    if (t.first_in_unit) {
+      const float* thr = s_thr + row_in_tile;
+      t31 = thr[31 * 128];
+      t15 = thr[15 * 128];
+      t47 = thr[47 * 128];
+      t7 = thr[7 * 128];
+      t23 = thr[23 * 128];
+      t39 = thr[39 * 128];
+      t55 = thr[55 * 128];
+    }
+  }
+
+  // slow path: full lexicographic bucket #{(t_k, p_k) <=lex (d, g)}
+  __device__ __noinline__ int tie_bucket(float d, int g) const {
+    int pos = 0;
+    for (int k = 0; k < nthr; ++k) {
+      const float tv = s_thr[k * 128 + row_in_tile];
+      if (tv < d || (tv == d && __ldg(p.thr_gidx + tbase + k) <= g)) pos = k + 1;
+    }
+    return pos;
   }
 
   __device__ void tile_body(const TileInfo& t, int as, uint32_t taddr) {
     const int row = t.m0 + row_in_tile;
     const bool active = nthr > 0;
+    if (!__any_sync(0xffffffffu, active)) return;  // whole warp beyond M / without positives
     const float na = active ? __ldg(p.a_norm + row) : 0.f;
     const float ia = active ? __ldg(p.a_inv + row) : 0.f;
-    const float* thr = s_thr + epi_tid;
-    unsigned* hist = s_hist + epi_tid;
+    const uint32_t thr0 = smem_u32(s_thr + row_in_tile);             // bucket b at thr0 + b*512
+    const uint32_t hist_delta = smem_u32(s_hist + hcol) - thr0;   // counter b at thr0 + delta + b*512
+    const float2* col = s_col + as * kBN + col0;
+    const int n_here = t.n_valid - col0;
+    constexpr int kC = 16;
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
-      uint32_t r[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-row branches
-      tmem_ld_32x32(taddr + c * 32, r);
+    for (int c = 0; c < kEpiCols / kC; ++c) {
+      if (c * kC >= n_here) break;  // warp-uniform
+      uint32_t r[kC];
+      __syncwarp();
+      tmem_ld_32x16(taddr + c * kC, r);
       tmem_ld_wait();
-      const int nv = min(32, t.n_valid - c * 32);
-      if (!active || nv <= 0) continue;
+      uint32_t slot[kC];   // shared address of the threshold row == bucket, per element
+      uint32_t ties = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j >= nv) continue;
-        const int cc = c * 32 + j;
-        const float dot = __uint_as_float(r[j]) * ia * cols.s_binv[as * kBN + cc];
-        const float d = fmaf(-2.f, dot, na + cols.s_bnorm[as * kBN + cc]);
-        int pos = 0;
-#pragma unroll
-        for (int step = 32; step >= 1; step >>= 1)
-          if (thr[(pos + step - 1) * kEpiThreads] <= d) pos += step;
-        if (pos > 0 && thr[(pos - 1) * kEpiThreads] == d) {
-          // exact tie with a threshold: thresholds with a larger gallery index come AFTER this column
-          const int g = __ldg(p.b_gidx + t.n0 + cc);
-          while (pos > 0 && thr[(pos - 1) * kEpiThreads] == d && __ldg(p.thr_gidx + tbase + pos - 1) > g) --pos;
-        }
-        hist[pos * kEpiThreads] += 1u;
+      for (int j = 0; j < kC; ++j) {
+        const float2 cm = col[c * kC + j];
+        const float d = fmaf(__uint_as_float(r[j]) * ia, cm.x, na + cm.y);
+        // level 1..3 from registers; `last` tracks the largest threshold <= d (tie detection)
+        const bool p1 = t31 <= d;
+        uint32_t a = p1 ? thr0 + 32 * kRowBytes : thr0;
+        float last = p1 ? t31 : -INFINITY;
+        const float u2 = p1 ? t47 : t15;
+        const bool p2 = u2 <= d;
+        a += p2 ? 16 * kRowBytes : 0;
+        last = p2 ? u2 : last;
+        const float hi3 = p2 ? t55 : t39, lo3 = p2 ? t23 : t7;
+        const float u3 = p1 ? hi3 : lo3;
+        const bool p3 = u3 <= d;
+        a += p3 ? 8 * kRowBytes : 0;
+        last = p3 ? u3 : last;
+        // level 4..6 from shared memory (immediate offsets, one predicated add per level)
+        float u = lds_f32_off<3 * kRowBytes>(a);
+        bool q = u <= d;
+        a += q ? 4 * kRowBytes : 0;
+        last = q ? u : last;
+        u = lds_f32_off<1 * kRowBytes>(a);
+        q = u <= d;
+        a += q ? 2 * kRowBytes : 0;
+        last = q ? u : last;
+        u = lds_f32_off<0>(a);
+        q = u <= d;
+        a += q ? 1 * kRowBytes : 0;
+        last = q ? u : last;
+        ties |= (last == d && d < INFINITY) ? (1u << j) : 0u;
+        slot[j] = a;
       }
+      if (ties && active) {
+        // exact tie with a threshold (rare): thresholds with a larger gallery index sort AFTER this column
+#pragma unroll
+        for (int j = 0; j < kC; ++j) {
+          if (ties >> j & 1u) {
+            const float2 cm = col[c * kC + j];
+            const float d = fmaf(__uint_as_float(r[j]) * ia, cm.x, na + cm.y);
+            slot[j] = thr0 + tie_bucket(d, __ldg(p.b_gidx + t.n0 + col0 + c * kC + j)) * kRowBytes;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kC; ++j) hist_inc_u16(slot[j] + hist_delta);
     }
   }
 
@@ -218,7 +309,7 @@ struct EpiCount {
     if (t.last_in_unit && nthr > 0) {
       unsigned run = 0;
       for (int k = 0; k < nthr; ++k) {
-        run += s_hist[k * kEpiThreads + epi_tid];
+        run += s_hist[k * kEpiThreads + hcol];
         if (run) atomicAdd(p.counts + tbase + k, run);
       }
     }
@@ -247,10 +338,10 @@ struct EpiExtract {
   };
   const Params& p;
   EpiColumns cols;
-  int epi_tid, row_in_tile;
+  int epi_tid, row_in_tile, col0;
 
-  __device__ EpiExtract(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_)
-      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_) {}
+  __device__ EpiExtract(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
+      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {}
 
   __device__ void tile_begin(const TileInfo& t, int as) {
     cols.stage(t, as, epi_tid, p.b_norm, p.b_inv, p.b_pid);
@@ -263,19 +354,23 @@ struct EpiExtract {
     const int pid = row_ok ? __ldg(p.a_pid + row) : 0;
     const int lo = row_ok ? __ldg(p.g_lo + row) : 0;
     const int base = row_ok ? __ldg(p.rec_base + row) : 0;
+    const float2* col = cols.s_col + as * kBN + col0;
+    const int* lab = cols.s_lab + as * kBN + col0;
+    const int n_here = t.n_valid - col0;
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int c = 0; c < kEpiCols / 32; ++c) {
+      if (c * 32 >= n_here) break;
       uint32_t r[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-row branches
+      __syncwarp();
       tmem_ld_32x32(taddr + c * 32, r);
       tmem_ld_wait();
       if (!row_ok) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int cc = c * 32 + j;
-        if (cc < t.n_valid && cols.s_blab[as * kBN + cc] == pid) {
-          const float dot = __uint_as_float(r[j]) * ia * cols.s_binv[as * kBN + cc];
-          p.rec_dist[base + (t.n0 + cc - lo)] = fmaf(-2.f, dot, na + cols.s_bnorm[as * kBN + cc]);
+        if (cc < n_here && lab[cc] == pid) {
+          const float2 cm = col[cc];
+          p.rec_dist[base + (t.n0 + col0 + cc - lo)] = fmaf(__uint_as_float(r[j]) * ia, cm.x, na + cm.y);
         }
       }
     }
@@ -306,10 +401,10 @@ struct EpiMine {
   };
   const Params& p;
   EpiColumns cols;
-  int epi_tid, row_in_tile;
+  int epi_tid, row_in_tile, col0;
 
-  __device__ EpiMine(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_)
-      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_) {}
+  __device__ EpiMine(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
+      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {}
 
   __device__ void tile_begin(const TileInfo& t, int as) {
     cols.stage(t, as, epi_tid, p.b_norm, p.b_inv, p.b_lab);
@@ -319,24 +414,28 @@ struct EpiMine {
     const bool row_ok = row < p.M;
     const float na = row_ok ? __ldg(p.a_norm + row) : 0.f;
     const float ia = row_ok ? __ldg(p.a_inv + row) : 0.f;
-    const int lab = row_ok ? __ldg(p.a_lab + row) : 0;
+    const int mylab = row_ok ? __ldg(p.a_lab + row) : 0;
+    const float2* col = cols.s_col + as * kBN + col0;
+    const int* lab = cols.s_lab + as * kBN + col0;
+    const int n_here = t.n_valid - col0;
     unsigned long long bp = 0ull, bn = ~0ull;
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int c = 0; c < kEpiCols / 32; ++c) {
+      if (c * 32 >= n_here) break;
       uint32_t r[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-row branches
+      __syncwarp();
       tmem_ld_32x32(taddr + c * 32, r);
       tmem_ld_wait();
       if (!row_ok) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int cc = c * 32 + j;
-        if (cc >= t.n_valid) continue;
-        const float dot = __uint_as_float(r[j]) * ia * cols.s_binv[as * kBN + cc];
-        const float d = finish_distance(DIST_SQRT, dot, na, cols.s_bnorm[as * kBN + cc]);
+        if (cc >= n_here) continue;
+        const float2 cm = col[cc];
+        const float d = sqrtf(fmaxf(fmaf(__uint_as_float(r[j]) * ia, cm.x, na + cm.y), 1e-12f));
         const unsigned key = float_key(d);
-        const unsigned idx = static_cast<unsigned>(t.n0 + cc);
-        if (cols.s_blab[as * kBN + cc] == lab) {
+        const unsigned idx = static_cast<unsigned>(t.n0 + col0 + cc);
+        if (lab[cc] == mylab) {
           const unsigned long long v = (static_cast<unsigned long long>(key) << 32) | (0xFFFFFFFFu - idx);
           bp = v > bp ? v : bp;
         } else {

@@ -8,7 +8,9 @@
 //   warp 0  TMA producer       (4 tile loads per k-block: A_hi, A_lo, B_hi, B_lo)
 //   warp 1  MMA issuer         (3 x BK/16 tcgen05.mma per k-block, one thread)
 //   warp 2  TMEM allocator
-//   warps 4-7  epilogue        (thread t of warp w owns accumulator row 32*(w%4)+t)
+//   warps 4-11 epilogue        (thread t of warp w owns accumulator row 32*(w%4)+t and the
+//                               column half (w-4)/4 of the tile: two warps per TMEM lane quadrant,
+//                               i.e. two epilogue warps per SM sub-partition to hide ALU latency)
 // The 128 x 256 fp32 accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue
 // of tile i overlaps the MMAs of tile i+1.  What the epilogue does with the distances is a
 // policy class (store / rank-count / extract-positives / hard-mining), see gemm_epilogues.cuh.
@@ -26,8 +28,9 @@ constexpr int kUmmaK = 16;          // K per tcgen05.mma (kind::f16)
 constexpr int kTileABytes = kBM * kBK * 2;
 constexpr int kTileBBytes = kBN * kBK * 2;
 constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // 48 KB
-constexpr int kGemmThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kEpiCols = kBN / 2;   // columns per epilogue thread
 constexpr int kTmemCols = 2 * kBN;  // 512: double-buffered accumulator
 
 // One unit of work: a fixed block of 128 A rows against `n_rows` consecutive B rows
@@ -102,8 +105,10 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Schedule sched, const int num_k_blocks, const typename Epi::Params ep) {
   constexpr int kStages = Epi::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // keep the pointer in the shared address space (plain pointer arithmetic, no integer round trip),
+  // otherwise every epilogue access degrades to a generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* bar_empty = bar_full + kStages;
   uint64_t* bar_tfull = bar_empty + kStages;
@@ -213,7 +218,8 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const int q = warp & 3;             // TMEM lane quadrant accessible to this warp
     const int row_in_tile = q * 32 + lane;
     const int epi_tid = threadIdx.x - (kGemmThreads - kEpiThreads);
-    Epi epi(ep, epi_smem, epi_tid, row_in_tile);
+    const int col0 = ((warp - 4) >> 2) * kEpiCols;  // this thread's column half of the tile
+    Epi epi(ep, epi_smem, epi_tid, row_in_tile, col0);
     int as = 0;
     uint32_t aphase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -230,7 +236,7 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         mbar_wait(&bar_tfull[as], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(as * kBN);
+                               static_cast<uint32_t>(as * kBN + col0);
         epi.tile_body(t, as, taddr);
         tc_fence_before();
         __syncwarp();
