@@ -44,6 +44,10 @@ SIGNATURES = {
                                  vp, vp, vp, vp, vp, vp, vp, vp]),
     "demo_eval_matrix": (i32, [vp, i32, i32, i64, vp, vp, vp, sz, i64, i32, i32, vp, sz, vp, vp, vp, vp, vp, vp]),
     "demo_eval_ws_pointers": (i32, [vp, sz, i32, i32, i32, i64] + [C.POINTER(vp)] * 13),
+    "demo_rerank_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
+    "demo_rerank": (i32, [vp, i32, i32, i32, i64, i32, i32, i32, C.c_double, vp, i64, i32, vp, i64, vp, vp, sz, vp]),
+    "demo_rerank_matrix": (i32, [vp, i64, i32, i32, i32, i32, C.c_double, vp, i64, vp, sz, vp]),
+    "demo_topk_rows": (i32, [vp, i32, i32, i64, i32, vp, vp, vp]),
 }
 
 _lib = None

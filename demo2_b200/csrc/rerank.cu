@@ -1,0 +1,578 @@
+// k-reciprocal re-ranking (utils/reranking.py:29-100) as sparse, row-local CUDA kernels.
+//
+// Notation.  E is the N x N matrix the ranking works on, N = Q + G.  With E[i][j] = X[j][i] where
+// X is the reference's `original_dist` before normalisation (:41-45), the reference's
+// `np.transpose(X / np.max(X, axis=0))` (:46) is  od[i][j] = E[i][j] / rowmax_i(E), so every
+// stage below is row-local in E.  (For the feature path E is simply our all-pairs GEMM output,
+// whose row maxima come fused from the GEMM epilogue.)
+//
+//   topk        rank[i][0..K)     K = max(k1+1, k2) smallest od[i][.] by (value, index)    (:48)
+//   krecip      V row i (sorted unique indices, fp16 softmax weights)                      (:51-71)
+//   expand      V_qe[i] = fp16(mean of V[rank[i][0..k2)]) -- fp32 sequential sum, /k2      (:73-78)
+//   invert      column lists of V_qe                                                        (:80-82)
+//   jaccard     per query: fp16 sequential accumulation over ascending columns, blend      (:84-99)
+//
+// Rounding contract: float32 exp, numpy pairwise float32 sum,
+// fp16 stores, numpy's "compute in float32, round once" half arithmetic.
+#include "rerank.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+namespace demo {
+
+namespace {
+
+// numpy half arithmetic: convert to float32, operate, round to half once
+__device__ __forceinline__ __half np_hadd(__half a, __half b) { return __float2half_rn(__half2float(a) + __half2float(b)); }
+__device__ __forceinline__ __half np_hsub(__half a, __half b) { return __float2half_rn(__half2float(a) - __half2float(b)); }
+__device__ __forceinline__ __half np_hmul(__half a, __half b) { return __float2half_rn(__half2float(a) * __half2float(b)); }
+__device__ __forceinline__ __half np_hdiv(__half a, __half b) { return __float2half_rn(__half2float(a) / __half2float(b)); }
+
+// numpy's pairwise float32 summation (numpy/core/src/umath/loops_utils.h.src pairwise_sum)
+__device__ float np_pairwise_sum(const float* a, int n) {
+  if (n < 8) {
+    float res = 0.f;
+    for (int i = 0; i < n; ++i) res += a[i];
+    return res;
+  }
+  if (n <= 128) {
+    float r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// ---------------------------------------------------------------------------------------
+// row max / transpose helpers (local_distmat paths)
+// ---------------------------------------------------------------------------------------
+__global__ void rowmax_kernel(const float* __restrict__ E, long long ld, int N, float* __restrict__ rowmax) {
+  const int i = blockIdx.x;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) m = fmaxf(m, E[(long long)i * ld + j]);
+  __shared__ float s[256];
+  s[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] = fmaxf(s[threadIdx.x], s[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rowmax[i] = s[0];
+}
+
+// E[i][j] (+)= X[j][i]
+__global__ void transpose_add_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ E, long long lde,
+                                     int N, int accumulate) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int j = by + r, i = bx + threadIdx.x;  // read X[j][i]
+    tile[r][threadIdx.x] = (j < N && i < N) ? X[(long long)j * ldx + i] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = bx + r, j = by + threadIdx.x;
+    if (i < N && j < N) {
+      float* dst = E + (long long)i * lde + j;
+      const float v = tile[threadIdx.x][r];
+      *dst = accumulate ? *dst + v : v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// top-k smallest per row by (value, index): radix select on ordered keys + bitonic sort of
+// the k winners.  One block per row; the row is read from HBM once and kept in shared memory.
+// ---------------------------------------------------------------------------------------
+constexpr int kTopkThreads = 256;
+
+template <bool kCached>
+__global__ void __launch_bounds__(kTopkThreads)
+topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const float* __restrict__ row_div, int k,
+                 int* __restrict__ idx_out, float* __restrict__ val_out) {
+  extern __shared__ unsigned s_dyn[];
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_prefix, s_need, s_nless, s_neq;
+  __shared__ unsigned long long s_cand[256];
+  unsigned* s_key = s_dyn;  // [cols] when cached
+  const int row = blockIdx.x;
+  const int t = threadIdx.x;
+  const float* src = mat + (long long)row * ld;
+  const float div = row_div ? row_div[row] : 1.f;
+  auto key_at = [&](int j) -> unsigned {
+    if (kCached) return s_key[j];
+    const float v = row_div ? src[j] / div : src[j];
+    return float_key(v + 0.f);
+  };
+  if (kCached) {
+    for (int j = t; j < cols; j += kTopkThreads) {
+      const float v = row_div ? src[j] / div : src[j];
+      s_key[j] = float_key(v + 0.f);  // +0: canonical zero
+    }
+  }
+  if (t == 0) {
+    s_prefix = 0;
+    s_need = k;
+  }
+  __syncthreads();
+  // 4 x 8-bit radix select for the k-th smallest key
+  for (int pass = 3; pass >= 0; --pass) {
+    s_hist[t] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned hi_mask = pass == 3 ? 0u : (0xFFFFFFFFu << ((pass + 1) * 8));
+    for (int j = t; j < cols; j += kTopkThreads) {
+      const unsigned key = key_at(j);
+      if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(key >> (pass * 8)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned need = s_need, cum = 0;
+      int b = 0;
+      for (; b < 256; ++b) {
+        if (cum + s_hist[b] >= need) break;
+        cum += s_hist[b];
+      }
+      s_need = need - cum;
+      s_prefix = prefix | (static_cast<unsigned>(b) << (pass * 8));
+    }
+    __syncthreads();
+  }
+  const unsigned kth = s_prefix;
+  const unsigned take_eq = s_need;  // how many of the keys == kth belong to the top-k (lowest indices)
+  if (t == 0) {
+    s_nless = 0;
+    s_neq = 0;
+  }
+  __syncthreads();
+  // keys < kth: any order (sorted below); keys == kth: first `take_eq` in index order
+  for (int j0 = 0; j0 < cols; j0 += kTopkThreads) {
+    const int j = j0 + t;
+    const unsigned key = j < cols ? key_at(j) : 0xFFFFFFFFu;
+    if (j < cols && key < kth) {
+      const unsigned p = atomicAdd(&s_nless, 1u);
+      s_cand[p] = (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned>(j);
+    }
+    // ordered compaction of the ties
+    const bool eq = j < cols && key == kth;
+    const unsigned ball = __ballot_sync(0xffffffffu, eq);
+    __shared__ unsigned s_wcnt[kTopkThreads / 32];
+    if ((t & 31) == 0) s_wcnt[t >> 5] = __popc(ball);
+    __syncthreads();
+    unsigned before = s_neq;
+    for (int w = 0; w < (t >> 5); ++w) before += s_wcnt[w];
+    before += __popc(ball & ((1u << (t & 31)) - 1u));
+    if (eq && before < take_eq)
+      s_cand[(k - take_eq) + before] = (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned>(j);
+    __syncthreads();
+    if (t == 0) {
+      unsigned tot = 0;
+      for (int w = 0; w < kTopkThreads / 32; ++w) tot += s_wcnt[w];
+      s_neq += tot;
+    }
+    __syncthreads();
+  }
+  // bitonic sort of the k candidates (padded to 256) by (key, index)
+  if (t >= k) s_cand[t] = ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= 256; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int partner = t ^ stride;
+      if (partner > t) {
+        const bool up = (t & size) == 0;
+        const unsigned long long a = s_cand[t], b = s_cand[partner];
+        if ((a > b) == up) {
+          s_cand[t] = b;
+          s_cand[partner] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (t < k) {
+    const unsigned long long c = s_cand[t];
+    idx_out[(long long)row * k + t] = static_cast<int>(c & 0xFFFFFFFFu);
+    if (val_out) val_out[(long long)row * k + t] = key_float(static_cast<unsigned>(c >> 32));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// bitmap helpers (block-wide)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void bm_set(unsigned* bm, int x) { atomicOr(&bm[x >> 5], 1u << (x & 31)); }
+__device__ __forceinline__ bool bm_get(const unsigned* bm, int x) { return (bm[x >> 5] >> (x & 31)) & 1u; }
+
+// Enumerate the set bits of bm[0..words) in ascending order into out[] (at most cap), returns
+// the total count.  All threads of the block must call.  s_scan: >= blockDim.x + 1 unsigned.
+__device__ int bm_enumerate(const unsigned* bm, int words, int* out, int cap, unsigned* s_scan) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int per = ceil_div(words, nt);
+  const int w0 = min(words, t * per), w1 = min(words, w0 + per);
+  unsigned c = 0;
+  for (int w = w0; w < w1; ++w) c += __popc(bm[w]);
+  s_scan[t + 1] = c;
+  if (t == 0) s_scan[0] = 0;
+  __syncthreads();
+  if (t == 0)
+    for (int i = 1; i <= nt; ++i) s_scan[i] += s_scan[i - 1];
+  __syncthreads();
+  unsigned pos = s_scan[t];
+  for (int w = w0; w < w1; ++w) {
+    unsigned bits = bm[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (pos < static_cast<unsigned>(cap)) out[pos] = w * 32 + b;
+      ++pos;
+    }
+  }
+  const int total = s_scan[nt];
+  __syncthreads();
+  return total;
+}
+
+// ---------------------------------------------------------------------------------------
+// k-reciprocal neighbours + expansion + softmax weights (one block per row)
+// ---------------------------------------------------------------------------------------
+constexpr int kKrThreads = 128;
+constexpr int kMaxK = 128;  // k1 + 1 <= kMaxK
+
+__global__ void __launch_bounds__(kKrThreads)
+krecip_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ rowmax,
+              const int* __restrict__ rank, int K, int N, int k1, int kh, int cap, int* __restrict__ v_idx,
+              __half* __restrict__ v_val, int* __restrict__ v_cnt) {
+  extern __shared__ unsigned s_dyn[];
+  const int words = ceil_div(N, 32);
+  unsigned* bm_kri = s_dyn;            // reciprocal set R(i, k1)
+  unsigned* bm_exp = s_dyn + words;    // expanded set
+  int* s_list = reinterpret_cast<int*>(s_dyn + 2 * words);  // [cap]
+  float* s_w = reinterpret_cast<float*>(s_list + cap);       // [cap]
+  __shared__ int s_fwd[kMaxK];
+  __shared__ int s_kri[kMaxK];
+  __shared__ int s_nkri;
+  __shared__ unsigned s_scan[kKrThreads + 1];
+  __shared__ float s_sum;
+  const int i = blockIdx.x, t = threadIdx.x;
+  const int K1 = k1 + 1;
+  for (int w = t; w < 2 * words; w += kKrThreads) s_dyn[w] = 0;
+  if (t < K1) s_fwd[t] = rank[(long long)i * K + t];
+  if (t == 0) s_nkri = 0;
+  __syncthreads();
+  // R(i, k1) = { f in fwd : i in rank[f][0..k1] }
+  if (t < K1) {
+    const int f = s_fwd[t];
+    const int* rf = rank + (long long)f * K;
+    bool found = false;
+    for (int m = 0; m < K1; ++m) found |= rf[m] == i;
+    if (found) {
+      s_kri[atomicAdd(&s_nkri, 1)] = f;
+      bm_set(bm_kri, f);
+      bm_set(bm_exp, f);
+    }
+  }
+  __syncthreads();
+  const int nkri = s_nkri;
+  // expansion: candidates c in R(i); R(c, k1/2); append when |R(c) & R(i)| > 2/3 |R(c)|
+  const int warp = t >> 5, lane = t & 31;
+  for (int ci = warp; ci < nkri; ci += kKrThreads / 32) {
+    const int c = s_kri[ci];
+    const int* rc = rank + (long long)c * K;
+    int len = 0, inter = 0;
+    unsigned member[kMaxK / 32] = {};  // which of cf[0..kh) are reciprocal, per lane-strided slot
+    for (int base = 0, slot = 0; base < kh; base += 32, ++slot) {
+      const int m = base + lane;
+      bool rec = false;
+      int x = -1;
+      if (m < kh) {
+        x = rc[m];
+        const int* rx = rank + (long long)x * K;
+        for (int mm = 0; mm < kh; ++mm) rec |= rx[mm] == c;
+      }
+      const unsigned ball = __ballot_sync(0xffffffffu, rec);
+      const unsigned ball_in = __ballot_sync(0xffffffffu, rec && bm_get(bm_kri, x));
+      len += __popc(ball);
+      inter += __popc(ball_in);
+      member[slot] = ball;
+    }
+    if (static_cast<double>(inter) > (2.0 / 3.0) * static_cast<double>(len)) {
+      for (int base = 0, slot = 0; base < kh; base += 32, ++slot) {
+        const int m = base + lane;
+        if (m < kh && ((member[slot] >> lane) & 1u)) bm_set(bm_exp, rc[m]);
+      }
+    }
+  }
+  __syncthreads();
+  const int n = bm_enumerate(bm_exp, words, s_list, cap, s_scan);  // np.unique: sorted ascending
+  const int nn = min(n, cap);
+  const float div = rowmax[i];
+  const float* erow = E + (long long)i * lde;
+  for (int p = t; p < nn; p += kKrThreads) s_w[p] = expf(-(erow[s_list[p]] / div));
+  __syncthreads();
+  if (t == 0) s_sum = np_pairwise_sum(s_w, nn);
+  __syncthreads();
+  const float sum = s_sum;
+  for (int p = t; p < nn; p += kKrThreads) {
+    v_idx[(long long)i * cap + p] = s_list[p];
+    v_val[(long long)i * cap + p] = __float2half_rn(s_w[p] / sum);
+  }
+  if (t == 0) v_cnt[i] = nn;
+}
+
+// ---------------------------------------------------------------------------------------
+// local query expansion: V_qe[i] = fp16(mean_m V[rank[i][m]]), m < k2 (one block per row)
+// ---------------------------------------------------------------------------------------
+constexpr int kQeThreads = 128;
+
+__global__ void __launch_bounds__(kQeThreads)
+expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const int* __restrict__ v_idx,
+              const __half* __restrict__ v_val, const int* __restrict__ v_cnt, int capq,
+              int* __restrict__ q_idx, __half* __restrict__ q_val, int* __restrict__ q_cnt) {
+  extern __shared__ unsigned s_dyn[];
+  const int words = ceil_div(N, 32);
+  unsigned* bm = s_dyn;
+  int* s_list = reinterpret_cast<int*>(s_dyn + words);  // [capq]
+  __shared__ unsigned s_scan[kQeThreads + 1];
+  __shared__ int s_nb[64];
+  const int i = blockIdx.x, t = threadIdx.x;
+  for (int w = t; w < words; w += kQeThreads) bm[w] = 0;
+  if (t < k2) s_nb[t] = rank[(long long)i * K + t];
+  __syncthreads();
+  for (int m = 0; m < k2; ++m) {
+    const int r = s_nb[m];
+    const int cnt = v_cnt[r];
+    for (int p = t; p < cnt; p += kQeThreads)
+      if (__half2float(v_val[(long long)r * cap + p]) != 0.f) bm_set(bm, v_idx[(long long)r * cap + p]);
+  }
+  __syncthreads();
+  const int n = bm_enumerate(bm, words, s_list, capq, s_scan);
+  const int nn = min(n, capq);
+  const float inv_k2_den = static_cast<float>(k2);
+  for (int p = t; p < nn; p += kQeThreads) {
+    const int col = s_list[p];
+    float acc = 0.f;
+    for (int m = 0; m < k2; ++m) {  // sequential float32 sum in neighbour order (np.mean over fp16 rows)
+      const int r = s_nb[m];
+      const int* ri = v_idx + (long long)r * cap;
+      int lo = 0, hi = v_cnt[r];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ri[mid] < col) lo = mid + 1; else hi = mid;
+      }
+      if (lo < v_cnt[r] && ri[lo] == col) acc += __half2float(v_val[(long long)r * cap + lo]);
+    }
+    q_idx[(long long)i * capq + p] = col;
+    q_val[(long long)i * capq + p] = __float2half_rn(acc / inv_k2_den);
+  }
+  if (t == 0) q_cnt[i] = nn;
+}
+
+// ---------------------------------------------------------------------------------------
+// inverted index (column lists; order inside a column is irrelevant)
+// ---------------------------------------------------------------------------------------
+__global__ void inv_count_kernel(const int* __restrict__ idx, const __half* __restrict__ val, const int* __restrict__ cnt,
+                                 int cap, int N, int* __restrict__ col_cnt) {
+  const int i = blockIdx.x;
+  const int c = cnt[i];
+  for (int p = threadIdx.x; p < c; p += blockDim.x)
+    if (__half2float(val[(long long)i * cap + p]) != 0.f) atomicAdd(&col_cnt[idx[(long long)i * cap + p]], 1);
+}
+__global__ void inv_fill_kernel(const int* __restrict__ idx, const __half* __restrict__ val, const int* __restrict__ cnt,
+                                int cap, int N, const int* __restrict__ inv_ofs, int* __restrict__ cursor,
+                                int* __restrict__ inv_row, __half* __restrict__ inv_val) {
+  const int i = blockIdx.x;
+  const int c = cnt[i];
+  for (int p = threadIdx.x; p < c; p += blockDim.x) {
+    const __half v = val[(long long)i * cap + p];
+    if (__half2float(v) != 0.f) {
+      const int col = idx[(long long)i * cap + p];
+      const int slot = inv_ofs[col] + atomicAdd(&cursor[col], 1);
+      inv_row[slot] = i;
+      inv_val[slot] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Jaccard distance + blend (one block per query row)
+// ---------------------------------------------------------------------------------------
+constexpr int kJcThreads = 256;
+
+__global__ void __launch_bounds__(kJcThreads)
+jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ rowmax, int N, int Q,
+               const int* __restrict__ idx, const __half* __restrict__ val, const int* __restrict__ cnt, int cap,
+               const int* __restrict__ inv_ofs, const int* __restrict__ inv_row, const __half* __restrict__ inv_val,
+               float one_minus_lambda_h, float lambda_f, __half* __restrict__ scratch, float* __restrict__ out,
+               long long ldo) {
+  extern __shared__ __half s_tmin[];
+  const int i = blockIdx.x, t = threadIdx.x;
+  __half* tmin = scratch ? scratch + (long long)i * N : s_tmin;
+  for (int j = t; j < N; j += kJcThreads) tmin[j] = __float2half_rn(0.f);
+  __syncthreads();
+  const int c = cnt[i];
+  for (int p = 0; p < c; ++p) {  // ascending column order (:89-93)
+    const __half vij = val[(long long)i * cap + p];
+    if (__half2float(vij) == 0.f) continue;  // block-uniform
+    const int col = idx[(long long)i * cap + p];
+    const int s = inv_ofs[col], e = inv_ofs[col + 1];
+    for (int q = s + t; q < e; q += kJcThreads) {
+      const int r = inv_row[q];
+      const __half m = __float2half_rn(fminf(__half2float(vij), __half2float(inv_val[q])));
+      tmin[r] = np_hadd(tmin[r], m);
+    }
+    __syncthreads();
+  }
+  const __half one = __float2half_rn(1.f), two = __float2half_rn(2.f);
+  const __half w = __float2half_rn(one_minus_lambda_h);
+  const float div = rowmax[i];
+  const int G = N - Q;
+  for (int g = t; g < G; g += kJcThreads) {
+    const __half tm = tmin[Q + g];
+    const __half jac = np_hsub(one, np_hdiv(tm, np_hsub(two, tm)));           // 1 - tmin / (2 - tmin)
+    const float od = E[(long long)i * lde + Q + g] / div;
+    out[(long long)i * ldo + g] = __half2float(np_hmul(jac, w)) + od * lambda_f;  // (:95)
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int launch_rowmax(const float* E, long long lde, int N, float* rowmax, cudaStream_t stream) {
+  rowmax_kernel<<<N, 256, 0, stream>>>(E, lde, N, rowmax);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  return DEMO_OK;
+}
+
+int launch_transpose_add(const float* X, long long ldx, float* E, long long lde, int N, bool accumulate,
+                         cudaStream_t stream) {
+  dim3 grid(ceil_div(N, 32), ceil_div(N, 32)), block(32, 8);
+  transpose_add_kernel<<<grid, block, 0, stream>>>(X, ldx, E, lde, N, accumulate ? 1 : 0);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  return DEMO_OK;
+}
+
+int launch_topk_rows(const float* mat, long long ld, int rows, int cols, const float* row_div, int k, int* idx_out,
+                     float* val_out, cudaStream_t stream) {
+  DEMO_REQUIRE(k >= 1 && k <= 256 && k <= cols, "topk: k=%d out of range (cols=%d, max 256)", k, cols);
+  if (rows <= 0) return DEMO_OK;
+  const size_t smem = static_cast<size_t>(cols) * 4;
+  if (smem <= 200 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      DEMO_CHECK_CUDA(cudaFuncSetAttribute(topk_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    topk_rows_kernel<true><<<rows, kTopkThreads, smem, stream>>>(mat, ld, cols, row_div, k, idx_out, val_out);
+  } else {
+    topk_rows_kernel<false><<<rows, kTopkThreads, 0, stream>>>(mat, ld, cols, row_div, k, idx_out, val_out);
+  }
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  return DEMO_OK;
+}
+
+int rerank_k(int k1, int k2) { return (k1 + 1 > k2 ? k1 + 1 : k2); }
+int rerank_kh(int k1) {
+  // int(np.around(k1 / 2)) + 1 with round-half-to-even (appendix A7)
+  const int half2 = k1;  // k1/2 = half2/2
+  int r = half2 / 2;
+  if (half2 % 2 == 1 && (r % 2 == 1)) r += 1;  // x.5 -> even
+  return r + 1;
+}
+int rerank_cap(int k1) { return (k1 + 1) * (rerank_kh(k1) + 1); }
+int rerank_capq(int N, int k1, int k2) {
+  const long long c = static_cast<long long>(k2 > 1 ? k2 : 1) * rerank_cap(k1);
+  return static_cast<int>(c < N ? c : N);
+}
+
+size_t rerank_carve(Carver& c, int N, int Q, int k1, int k2, RerankWs* w) {
+  RerankWs t;
+  const size_t n = N > 0 ? N : 1;
+  t.K = rerank_k(k1, k2);
+  t.cap = rerank_cap(k1);
+  t.capq = rerank_capq(N, k1, k2);
+  t.rank = c.take<int>(n * t.K);
+  t.v_idx = c.take<int>(n * t.cap);
+  t.v_val = c.take<__half>(n * t.cap);
+  t.v_cnt = c.take<int>(n);
+  t.q_idx = c.take<int>(n * t.capq);
+  t.q_val = c.take<__half>(n * t.capq);
+  t.q_cnt = c.take<int>(n);
+  t.col_cnt = c.take<int>(n + 1);
+  t.inv_ofs = c.take<int>(n + 1);
+  t.cursor = c.take<int>(n + 1);
+  t.inv_row = c.take<int>(n * t.capq);
+  t.inv_val = c.take<__half>(n * t.capq);
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, t.col_cnt, t.inv_ofs, N + 1);
+  t.cub_bytes = tmp + 256;
+  t.cub_tmp = c.take<char>(t.cub_bytes);
+  t.tmin_scratch = nullptr;
+  t.tmin_bytes = 0;
+  if (static_cast<size_t>(N) * 2 > 200 * 1024) {  // temp_min does not fit shared memory
+    const size_t q = Q > 0 ? Q : 1;
+    t.tmin_bytes = q * n * 2;
+    t.tmin_scratch = c.take<__half>(q * n);
+  }
+  if (w) *w = t;
+  return c.off;
+}
+
+int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N, int Q, int k1, int k2,
+                      double lambda_value, const RerankWs& w, float* out, long long ldo, cudaStream_t stream) {
+  DEMO_REQUIRE(k1 >= 1 && k1 + 1 <= kMaxK && k1 + 1 <= N, "re_ranking: need 1 <= k1 < min(N, %d) (k1=%d, N=%d)", kMaxK, k1, N);
+  DEMO_REQUIRE(k2 >= 1 && k2 <= 64 && k2 <= N, "re_ranking: need 1 <= k2 <= min(N, 64) (k2=%d)", k2);
+  DEMO_REQUIRE(Q >= 1 && Q < N, "re_ranking: need 1 <= Q < N");
+  const int K = w.K, kh = rerank_kh(k1), words = ceil_div(N, 32);
+  DEMO_TRY(launch_topk_rows(E, lde, N, N, rowmax, K, w.rank, nullptr, stream));
+  {
+    const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(w.cap) * 8;
+    DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d too large for the shared-memory bitmaps", N);
+    DEMO_CHECK_CUDA(cudaFuncSetAttribute(krecip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    krecip_kernel<<<N, kKrThreads, smem, stream>>>(E, lde, rowmax, w.rank, K, N, k1, kh, w.cap, w.v_idx, w.v_val, w.v_cnt);
+    DEMO_CHECK_CUDA(cudaGetLastError());
+  }
+  const int* f_idx = w.v_idx;
+  const __half* f_val = w.v_val;
+  const int* f_cnt = w.v_cnt;
+  int f_cap = w.cap;
+  if (k2 != 1) {
+    const size_t smem = static_cast<size_t>(words) * 4 + static_cast<size_t>(w.capq) * 4;
+    DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d / k2=%d too large for the expansion kernel", N, k2);
+    DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    expand_kernel<<<N, kQeThreads, smem, stream>>>(w.rank, K, N, k2, w.cap, w.v_idx, w.v_val, w.v_cnt, w.capq, w.q_idx,
+                                                   w.q_val, w.q_cnt);
+    DEMO_CHECK_CUDA(cudaGetLastError());
+    f_idx = w.q_idx;
+    f_val = w.q_val;
+    f_cnt = w.q_cnt;
+    f_cap = w.capq;
+  }
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int) * (N + 1), stream));
+  inv_count_kernel<<<N, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, N, w.col_cnt);
+  size_t tmp = w.cub_bytes;
+  DEMO_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.col_cnt, w.inv_ofs, N + 1, stream));
+  inv_fill_kernel<<<N, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, N, w.inv_ofs, w.cursor, w.inv_row, w.inv_val);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  {
+    // (1 - lambda) is a Python float: numpy multiplies the fp16 array by fp16(1 - lambda)
+    const float oml = __half2float(__double2half(1.0 - lambda_value));
+    const size_t smem = w.tmin_scratch ? 0 : static_cast<size_t>(N) * 2;
+    DEMO_CHECK_CUDA(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    jaccard_kernel<<<Q, kJcThreads, smem, stream>>>(E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w.inv_ofs, w.inv_row,
+                                                    w.inv_val, oml, static_cast<float>(lambda_value), w.tmin_scratch, out,
+                                                    ldo);
+    DEMO_CHECK_CUDA(cudaGetLastError());
+  }
+  return DEMO_OK;
+}
+
+}  // namespace demo

@@ -1,0 +1,42 @@
+// k-reciprocal re-ranking stages (see rerank.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace demo {
+
+struct RerankWs {
+  int K = 0, cap = 0, capq = 0;
+  int* rank = nullptr;       // [N][K]
+  int* v_idx = nullptr;      // [N][cap]   V rows before expansion
+  __half* v_val = nullptr;
+  int* v_cnt = nullptr;      // [N]
+  int* q_idx = nullptr;      // [N][capq]  V rows after local query expansion
+  __half* q_val = nullptr;
+  int* q_cnt = nullptr;
+  int* col_cnt = nullptr;    // [N+1]
+  int* inv_ofs = nullptr;    // [N+1]
+  int* cursor = nullptr;     // [N+1]
+  int* inv_row = nullptr;    // [N*capq]
+  __half* inv_val = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  __half* tmin_scratch = nullptr;  // [Q][N] only when N*2 bytes exceed shared memory
+  size_t tmin_bytes = 0;
+};
+
+int rerank_k(int k1, int k2);
+int rerank_kh(int k1);
+int rerank_cap(int k1);
+int rerank_capq(int N, int k1, int k2);
+size_t rerank_carve(Carver& c, int N, int Q, int k1, int k2, RerankWs* w);
+
+int launch_rowmax(const float* E, long long lde, int N, float* rowmax, cudaStream_t stream);
+int launch_transpose_add(const float* X, long long ldx, float* E, long long lde, int N, bool accumulate,
+                         cudaStream_t stream);
+int launch_topk_rows(const float* mat, long long ld, int rows, int cols, const float* row_div, int k, int* idx_out,
+                     float* val_out, cudaStream_t stream);
+int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N, int Q, int k1, int k2,
+                      double lambda_value, const RerankWs& w, float* out, long long ldo, cudaStream_t stream);
+
+}  // namespace demo

@@ -118,6 +118,23 @@ DEMO_API int demo_eval_ws_pointers(void* ws, size_t ws_bytes, int Q, int G, int 
                                    int** thr_cnt, float** thr_val, int** thr_gidx, int** thr_junk,
                                    float** rec_dist, int** rec_gidx, int** rec_junk);
 
+/* ---- k-reciprocal re-ranking and top-k ----------------------------------------------------
+ * demo_rerank replaces re_ranking(probFea, galFea, k1, k2, lambda_value, local_distmat=None,
+ * only_local=False) (utils/reranking.py:29-100): feat = cat(probFea, galFea) [N][d],
+ * out [Q][N-Q] fp32.  float16 stores / adds follow the reference.
+ * demo_rerank_matrix starts from the all-pairs matrix X (the reference's original_dist before
+ * :46), which also serves the distance-matrix form re_ranking(q_g, q_q, g_g, k1, k2, lambda).
+ * demo_topk_rows: k smallest per row ascending by (value, column), k <= 256
+ * (np.argsort(...)[:, :k] at utils/reranking.py:48 and utils/metrics.py:279). */
+DEMO_API size_t demo_rerank_workspace_bytes(int N, int Q, int d, int k1, int k2);
+DEMO_API int demo_rerank(const float* feat, int N, int Q, int d, int64_t ld, int flags, int k1, int k2,
+                         double lambda_value, const float* local_distmat, int64_t ld_local, int only_local,
+                         float* out, int64_t ldo, float* feat_n_out, void* ws, size_t ws_bytes, void* stream);
+DEMO_API int demo_rerank_matrix(const float* X, int64_t ldx, int N, int Q, int k1, int k2, double lambda_value,
+                                float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
+DEMO_API int demo_topk_rows(const float* mat, int rows, int cols, int64_t ld, int k, int* idx_out,
+                            float* val_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

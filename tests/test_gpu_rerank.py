@@ -1,0 +1,122 @@
+"""GPU parity of k-reciprocal re-ranking and top-k against the CPU oracle and the reference's
+golden vectors.  The oracle is fed OUR all-pairs distance matrix so every downstream stage
+(top-k, reciprocal sets, fp16 V / query expansion / Jaccard / blend) is compared without GEMM
+rounding in between."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden, make_case, oracle, sample_index
+
+pytestmark = pytest.mark.gpu
+
+# One float16 quantum of the Jaccard term (values in [0.5, 1]) times (1 - lambda):
+# CUDA expf and numpy's SIMD exp differ by <= 2 ulp, which very rarely moves a V entry by one
+# fp16 ulp (0-4 of 698 896 entries).
+FP16_QUANTUM = 2.0 ** -11
+
+
+@pytest.fixture(scope="module")
+def R():
+    from demo2_b200 import reranking
+    return reranking
+
+
+@pytest.fixture(scope="module")
+def M():
+    from demo2_b200 import metrics
+    return metrics
+
+
+def _check_against_oracle(ours, expect):
+    assert ours.shape == expect.shape and ours.dtype == np.float32
+    diff = np.abs(ours - expect)
+    exact = (ours == expect).mean()
+    assert exact > 0.9995, exact
+    assert diff.max() <= 4 * FP16_QUANTUM, diff.max()
+
+
+def test_topk_matches_stable_argsort(R):
+    rng = np.random.default_rng(0)
+    for rows, cols, k in [(7, 50, 50), (33, 1000, 21), (5, 10290, 51), (3, 70000, 16)]:
+        m = rng.standard_normal((rows, cols)).astype(np.float32)
+        m[:, ::7] = np.round(m[:, ::7], 1)          # plenty of exact ties
+        m[0, :] = 1.0                                # a constant row
+        idx, val = R.topk_rows(m, k, want_values=True)
+        ref = np.argsort(m, axis=1, kind="stable")[:, :k]
+        np.testing.assert_array_equal(idx.cpu().numpy(), ref)
+        np.testing.assert_array_equal(val.cpu().numpy(), np.take_along_axis(m, ref, 1))
+
+
+@pytest.mark.parametrize("k1,k2", [(20, 6), (50, 15), (20, 1), (7, 3)])
+def test_rerank_stages_bit_level(R, M, k1, k2):
+    qf, gf, *_ = make_case("rgbnt201", 0, 5.0)
+    qf, gf = qf[:256], gf[:320]
+    feat = np.concatenate([qf, gf])
+    D = M.sqdist_device(feat, feat).cpu().numpy()
+    ours = R.re_ranking(qf, gf, k1, k2, 0.3)
+    # our E[i][j] plays the role of original_dist[j][i] (see csrc/rerank.cu header)
+    expect = oracle.re_ranking_from_allpairs(D.T, 256, k1, k2, 0.3)
+    _check_against_oracle(ours, expect)
+
+
+def test_rerank_full_size_vs_oracle_and_golden(R, M):
+    qf, gf, qp, gp, qc, gc = make_case("rgbnt201", 0, 5.0)
+    feat = np.concatenate([qf, gf])
+    D = M.sqdist_device(feat, feat).cpu().numpy()
+    ours = R.re_ranking(qf, gf, 20, 6, 0.3)
+    expect = oracle.re_ranking_from_allpairs(D.T, len(qf), 20, 6, 0.3)
+    _check_against_oracle(ours, expect)
+    # identical matrix -> metrics equal up to the handful of fp16-quantum entries
+    cmc, mAP = M.eval_func(ours, qp, gp, qc, gc)
+    cmc_o, mAP_o = oracle.eval_func(expect, qp, gp, qc, gc)
+    assert abs(mAP - mAP_o) < 1e-5
+    # against the reference run (different fp32 GEMM -> a few neighbour sets flip, see
+    # tests/test_oracle_golden.py)
+    g = load_golden("rerank_rgbnt201_s0_k20_6")
+    assert abs(mAP - float(g["mAP"])) < 2e-4
+    np.testing.assert_allclose(cmc, g["cmc"], atol=2.5 / len(qp))
+    si = sample_index(*ours.shape)
+    close = np.abs(ours.ravel()[si] - g["dist_sample"]) <= 1e-5 * np.abs(g["dist_sample"]) + 2e-6
+    assert close.mean() > 0.97
+
+
+def test_rerank_matrix_form_and_local(R):
+    """Distance-matrix form on the REFERENCE's all-pairs matrix reproduces the reference's
+    final distances (no GEMM involved); local_distmat / only_local paths."""
+    g = load_golden("fullmat_rgbnt201_256x320")
+    X = g["allpairs"]
+    Q = 256
+    for k1, k2 in ((20, 6), (50, 15), (20, 1), (7, 3)):
+        ours = R.re_ranking(X[:Q, Q:], X[:Q, :Q], X[Q:, Q:], k1, k2, 0.3)
+        _check_against_oracle(ours, g["final_%d_%d" % (k1, k2)])
+    gl = load_golden("rerank_local_200x300")
+    qf, gf, *_ = make_case("rgbnt201", 3, 5.0)
+    qf, gf = qf[:200], gf[:300]
+    rng = np.random.default_rng(7)
+    loc = rng.random((500, 500), dtype=np.float32)
+    loc = (loc + loc.T).astype(np.float32)
+    only = R.re_ranking(qf, gf, 20, 6, 0.3, local_distmat=loc, only_local=True)
+    _check_against_oracle(only, gl["only_local"])
+    both = R.re_ranking(qf, gf, 20, 6, 0.3, local_distmat=loc)
+    close = np.abs(both - gl["with_local"]) <= 1e-5 * np.abs(gl["with_local"]) + 2e-6
+    assert close.mean() > 0.99
+
+
+def test_evaluator_with_reranking(M):
+    from demo2_b200 import synth
+    g = load_golden("evaluator_rgbnt201_s0_sigma5")
+    s = synth.make_named("rgbnt201", sigma=5.0, seed=0)
+    feats = torch.cat([s.qf, s.gf])
+    pids = np.concatenate([s.q_pids, s.g_pids])
+    cams = np.concatenate([s.q_camids, s.g_camids])
+    ev = M.R1_mAP_eval(s.num_query, max_rank=50, feat_norm=True, reranking=True)
+    for b in range(0, feats.shape[0], 256):
+        ev.update((feats[b:b + 256].cuda(), tuple(int(p) for p in pids[b:b + 256]),
+                   torch.from_numpy(cams[b:b + 256]), ["x"] * len(pids[b:b + 256])))
+    cmc, mAP, distmat, *_ = ev.compute()          # k1=50, k2=15, lambda=0.3 as in the reference
+    assert distmat.shape == (836, 836)
+    assert abs(mAP - float(g["rr_mAP"])) < 2e-4
+    np.testing.assert_allclose(cmc, g["rr_cmc"], atol=2.5 / 836)
