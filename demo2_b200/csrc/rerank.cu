@@ -436,7 +436,7 @@ jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restri
     const __half tm = tmin[Q + g];
     const __half jac = np_hsub(one, np_hdiv(tm, np_hsub(two, tm)));           // 1 - tmin / (2 - tmin)
     const float od = E[(long long)i * lde + Q + g] / div;
-    out[(long long)i * ldo + g] = __half2float(np_hmul(jac, w)) + od * lambda_f;  // (:95)
+    out[(long long)i * ldo + g] = __fadd_rn(__half2float(np_hmul(jac, w)), __fmul_rn(od, lambda_f));  // (:95), no FMA contraction
   }
 }
 
