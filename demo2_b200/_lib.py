@@ -48,6 +48,10 @@ SIGNATURES = {
     "demo_rerank": (i32, [vp, i32, i32, i32, i64, i32, i32, i32, C.c_double, vp, i64, i32, vp, i64, vp, vp, sz, vp]),
     "demo_rerank_matrix": (i32, [vp, i64, i32, i32, i32, i32, C.c_double, vp, i64, vp, sz, vp]),
     "demo_topk_rows": (i32, [vp, i32, i32, i64, i32, vp, vp, vp]),
+    "demo_triplet_workspace_bytes": (sz, [i32, i32]),
+    "demo_triplet_hard_fwd": (i32, [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "demo_triplet_hard_bwd": (i32, [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "demo_hard_example_mining": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -135,6 +135,27 @@ DEMO_API int demo_rerank_matrix(const float* X, int64_t ldx, int N, int Q, int k
 DEMO_API int demo_topk_rows(const float* mat, int rows, int cols, int64_t ld, int k, int* idx_out,
                             float* val_out, void* stream);
 
+/* ---- batch-hard triplet mining -------------------------------------------------------------
+ * demo_triplet_hard_fwd replaces the core of TripletLoss.__call__ (layers/triplet_loss.py:124-125):
+ * euclidean_dist(x, x) + hard_example_mining(dist_mat, labels, return_inds=True) fused into the
+ * distance GEMM epilogue (the N x N matrix is never written).  Positives include the anchor
+ * itself (as in the reference); ties go to the lowest index; npos (optional) = #same-label
+ * samples per anchor so the host can reproduce the reference's equal-count requirement (:79).
+ * demo_triplet_hard_bwd: d loss / d x from the upstream gradients of dist_ap / dist_an (only the
+ * 2N selected pairs carry gradient).  demo_hard_example_mining: the same selection on a
+ * caller-provided distance matrix (layers/triplet_loss.py:51-104). */
+DEMO_API size_t demo_triplet_workspace_bytes(int N, int d);
+DEMO_API int demo_triplet_hard_fwd(const float* x, int N, int d, int64_t ld, const int* labels, float* dist_ap,
+                                   float* dist_an, int64_t* p_idx, int64_t* n_idx, int* npos, void* ws,
+                                   size_t ws_bytes, void* stream);
+DEMO_API int demo_triplet_hard_bwd(const float* x, int N, int d, int64_t ld, const int64_t* p_idx,
+                                   const int64_t* n_idx, const float* dist_ap, const float* dist_an,
+                                   const float* g_ap, const float* g_an, float* grad_x, int64_t ldg,
+                                   void* stream);
+DEMO_API int demo_hard_example_mining(const float* dist_mat, int N, int64_t ld, const int* labels,
+                                      float* dist_ap, float* dist_an, int64_t* p_idx, int64_t* n_idx,
+                                      int* npos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

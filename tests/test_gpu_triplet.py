@@ -1,0 +1,121 @@
+"""GPU parity of the triplet path (layers/triplet_loss.py) against the reference's golden
+vectors, the oracle, and a plain PyTorch fp32 restatement with autograd (floating-point kernel)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden, oracle
+
+from demo2_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+# distances ~ 39 on un-normalised 768-d rows: fp32 round-off of |x|^2+|y|^2-2xy is ~1e-4 absolute
+# on the SQUARED distance; 1e-5 relative on the distance (BASELINE.json) holds away from d ~ 0.
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def T():
+    from demo2_b200 import triplet_loss
+    return triplet_loss
+
+
+def torch_ref_loss(x, labels, margin=None, hard_factor=0.0, normalize_feature=False):
+    """Plain PyTorch fp32 restatement of TripletLoss.__call__ (autograd reference)."""
+    if normalize_feature:
+        x = x / (x.norm(dim=-1, keepdim=True) + 1e-12)
+    xx = x.pow(2).sum(1, keepdim=True)
+    d = (xx + xx.t() - 2 * x @ x.t()).clamp(min=1e-12).sqrt()
+    pos = labels[:, None] == labels[None, :]
+    ap = torch.where(pos, d, torch.full_like(d, -1e30)).max(1)[0] * (1.0 + hard_factor)
+    an = torch.where(~pos, d, torch.full_like(d, 1e30)).min(1)[0] * (1.0 - hard_factor)
+    if margin is not None:
+        loss = torch.relu(ap - an + margin).mean()
+    else:
+        loss = torch.nn.functional.softplus(-(an - ap)).mean()
+    return loss, ap, an
+
+
+def test_forward_matches_reference_golden(T):
+    g = load_golden("triplet_pk8x16_d768")
+    xs, labels = synth.make_triplet_batch()
+    for m, x in enumerate(xs):
+        ap, an, pi, ni = T.fused_hard_mining(x.cuda(), labels.cuda())
+        np.testing.assert_array_equal(pi.cpu().numpy(), g["pi%d" % m])
+        np.testing.assert_array_equal(ni.cpu().numpy(), g["ni%d" % m])
+        np.testing.assert_allclose(ap.cpu().numpy(), g["ap%d" % m], rtol=RTOL)
+        np.testing.assert_allclose(an.cpu().numpy(), g["an%d" % m], rtol=RTOL)
+        loss, ap2, an2 = T.TripletLoss()(x.cuda(), labels.cuda())
+        np.testing.assert_allclose(loss.item(), g["loss%d" % m], rtol=1e-5)
+        lossm, apm, anm = T.TripletLoss(margin=0.3, hard_factor=0.1)(x.cuda(), labels.cuda(), normalize_feature=True)
+        np.testing.assert_allclose(lossm.item(), g["lossm%d" % m], rtol=1e-5)
+        np.testing.assert_allclose(apm.cpu().numpy(), g["apm%d" % m], rtol=1e-4)
+        # free functions with the reference's signatures
+        d = T.euclidean_dist(x.cuda(), x.cuda())
+        np.testing.assert_allclose(d.cpu().numpy().ravel()[::37] ** 2, g["dist_sample%d" % m] ** 2, rtol=2e-5, atol=1e-3)
+        np.testing.assert_allclose(T.cosine_dist(x.cuda(), x.cuda()).cpu().numpy().ravel()[::37],
+                                   g["cos_sample%d" % m], rtol=1e-5, atol=1e-6)
+        ap3, an3, pi3, ni3 = T.hard_example_mining(d, labels.cuda(), return_inds=True)
+        assert pi3.dtype == torch.int64
+        # the materialised matrix has noise on the diagonal; off-diagonal selections agree
+        np.testing.assert_array_equal(pi3.cpu().numpy(), g["pi%d" % m])
+        np.testing.assert_array_equal(ni3.cpu().numpy(), g["ni%d" % m])
+
+
+def test_backward_matches_reference_and_torch(T):
+    g = load_golden("triplet_pk8x16_d768")
+    xs, labels = synth.make_triplet_batch()
+    for m, x in enumerate(xs):
+        xr = x.cuda().requires_grad_(True)
+        loss, _, _ = T.TripletLoss()(xr, labels.cuda())
+        loss.backward()
+        np.testing.assert_allclose(xr.grad.cpu().numpy(), g["grad%d" % m], rtol=1e-4, atol=1e-7)
+        xm = x.cuda().requires_grad_(True)
+        lossm, _, _ = T.TripletLoss(margin=0.3, hard_factor=0.1)(xm, labels.cuda(), normalize_feature=True)
+        lossm.backward()
+        np.testing.assert_allclose(xm.grad.cpu().numpy(), g["gradm%d" % m], rtol=2e-4, atol=1e-7)
+        # plain torch fp32 reference on the same device
+        xt = x.cuda().requires_grad_(True)
+        lt, _, _ = torch_ref_loss(xt, labels.cuda())
+        lt.backward()
+        np.testing.assert_allclose(loss.item(), lt.item(), rtol=1e-5)
+        np.testing.assert_allclose(xr.grad.cpu().numpy(), xt.grad.cpu().numpy(), rtol=1e-4, atol=1e-7)
+        # oracle gradient
+        np.testing.assert_allclose(xr.grad.cpu().numpy(), oracle.triplet_loss_grad(x.numpy(), labels.numpy()),
+                                   rtol=1e-4, atol=1e-7)
+
+
+def test_euclidean_dist_autograd_and_odd_batches(T):
+    torch.manual_seed(0)
+    x = torch.randn(37, 100, device="cuda", requires_grad=True)
+    y = torch.randn(53, 100, device="cuda", requires_grad=True)
+    d = T.euclidean_dist(x, y)
+    w = torch.randn_like(d)
+    (d * w).sum().backward()
+    x2, y2 = x.detach().clone().requires_grad_(True), y.detach().clone().requires_grad_(True)
+    d2 = (x2.pow(2).sum(1, keepdim=True) + y2.pow(2).sum(1, keepdim=True).t() - 2 * x2 @ y2.t()).clamp(min=1e-12).sqrt()
+    (d2 * w).sum().backward()
+    np.testing.assert_allclose(d.detach().cpu().numpy(), d2.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), x2.grad.cpu().numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(y.grad.cpu().numpy(), y2.grad.cpu().numpy(), rtol=1e-3, atol=1e-4)
+    # a batch larger than one tile in both directions (3 ids x 100 instances), CPU inputs
+    labels = torch.arange(3).repeat_interleave(100)
+    xb = torch.randn(300, 64)
+    ap, an, pi, ni = T.fused_hard_mining(xb, labels)
+    do = oracle.euclidean_dist(xb.numpy(), xb.numpy())
+    ap_o, an_o, pi_o, ni_o = oracle.hard_example_mining(do, labels.numpy(), return_inds=True)
+    np.testing.assert_allclose(ap.cpu().numpy(), ap_o, rtol=1e-5)
+    np.testing.assert_allclose(an.cpu().numpy(), an_o, rtol=1e-5)
+    assert (pi.cpu().numpy() == pi_o).mean() > 0.99 and (ni.cpu().numpy() == ni_o).mean() > 0.99
+
+
+def test_unequal_positives_raise(T):
+    x = torch.randn(6, 16, device="cuda")
+    labels = torch.tensor([0, 0, 0, 1, 1, 2], device="cuda")
+    with pytest.raises(RuntimeError):
+        T.TripletLoss()(x, labels)
+    with pytest.raises(RuntimeError):
+        T.hard_example_mining(T.euclidean_dist(x, x), labels)
