@@ -163,6 +163,37 @@ static void bench(int Q, int G, int d, int iters) {
   cudaFree(dq); cudaFree(dg); cudaFree(dout); cudaFree(ws);
 }
 
+// Accuracy on near-duplicate pairs (high cosine): A == B, report the self-distance error and the
+// dot-product relative error as a function of d.
+static void self_case(int n, int d, bool normalise) {
+  std::vector<float> h;
+  make_rows(h, n, d, 4242, normalise, 0.0f);
+  float *dx, *dout;
+  CK(cudaMalloc(&dx, h.size() * 4));
+  CK(cudaMalloc(&dout, (size_t)n * n * 4));
+  CK(cudaMemcpy(dx, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  size_t wsb = demo_sqdist_workspace_bytes(n, n, d, DEMO_FLAG_SIMT);
+  void* ws;
+  CK(cudaMalloc(&ws, wsb));
+  for (int simt = 0; simt < 2; ++simt) {
+    DK(demo_sqdist_f32(dx, dx, n, n, d, d, d, dout, n, simt ? DEMO_FLAG_SIMT : 0, nullptr, nullptr, nullptr, ws, wsb, nullptr));
+    CK(cudaDeviceSynchronize());
+    std::vector<float> out((size_t)n * n);
+    CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+    double worst = 0, mean = 0, norm2 = 0;
+    for (int i = 0; i < n; ++i) {
+      double s = 0;
+      for (int k = 0; k < d; ++k) s += (double)h[(size_t)i * d + k] * h[(size_t)i * d + k];
+      norm2 += s / n;
+      worst = std::max(worst, std::fabs((double)out[(size_t)i * n + i]));
+      mean += out[(size_t)i * n + i] / (double)n;
+    }
+    printf("self-distance n=%d d=%d norm=%d %s: |x|^2=%.3g  max|d_ii| %.3e  mean d_ii %.3e  (relative to 2|x|^2: %.2e)\n", n, d,
+           (int)normalise, simt ? "simt" : "tc  ", norm2, worst, mean, worst / (2 * norm2));
+  }
+  cudaFree(dx); cudaFree(dout); cudaFree(ws);
+}
+
 int main(int argc, char** argv) {
   if (!demo_device_ok()) {
     printf("no sm_100 device\n");
@@ -180,6 +211,11 @@ int main(int argc, char** argv) {
   ok &= run_case(130, 515, 520, false, 1.0f, DEMO_DIST_COS_DIST, 0);
   ok &= run_case(1715, 8575, 1536, true, 0.3f, DEMO_DIST_SQ, 100000);
   printf(ok ? "ALL CASES PASS\n" : "SOME CASES FAILED\n");
+  self_case(256, 64, true);
+  self_case(256, 512, true);
+  self_case(256, 1536, true);
+  self_case(256, 4096, true);
+  self_case(128, 768, false);
   if (argc > 1) {
     bench(1672, 1672, 1536, 20);
     bench(10290, 10290, 1536, 10);
