@@ -122,7 +122,7 @@ def cpu_eval_chunk(oracle, qf, gf_n, qp, gp, qc, gc):
     independently, so chunking is exact): normalise -> euclidean_distance -> eval_func."""
     qn = oracle.l2_normalize(qf)
     dist = oracle.euclidean_distance(qn, gf_n)
-    return oracle.eval_func(dist, qp, gp, qc, gc)
+    return oracle.eval_func(dist, qp, gp, qc, gc, sort_kind=None)  # the reference's default argsort
 
 
 def run_reference(args):
@@ -152,7 +152,7 @@ def run_reference(args):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = chunk / (ms * 1e-3)
-    sample = ("%d-query chunk x full %d gallery per step (normalise + fp32 sgemm distance + stable argsort + "
+    sample = ("%d-query chunk x full %d gallery per step (normalise + fp32 sgemm distance + np.argsort + "
               "per-query CMC/AP loop, oracle port of utils/metrics.py:110-169,341-401; gallery normalised once "
               "outside the timed step)" % (chunk, G))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -308,9 +308,69 @@ def run_ours(args):
                 "stage_ms": stage_ms}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(name, q_host, g_host, q_pid, g_pid, q_cam, g_cam)
+        if world == 1 and not args.no_other:
+            del q_host, g_host
+            try:
+                line["other_workloads"] = other_workloads(dev)
+            except Exception as exc:  # never lose the headline line
+                line["other_workloads"] = {"error": repr(exc)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_workloads(dev):
+    """The remaining BASELINE.json configs on one GPU (device-resident inputs, CUDA-event time of
+    the whole public-API call including the D2H of the metrics): latency-bound sizes, reported
+    as ms and queries/s next to the headline."""
+    import torch
+    from demo2_b200 import metrics, reranking, synth, triplet_loss
+
+    def timed(fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, out
+
+    res = {}
+    for key, shape, sigma in (("rgbnt201", "rgbnt201", 4.0), ("rgbnt100", "rgbnt100", 4.0)):
+        s = synth.make_named(shape, sigma=sigma, seed=0)
+        qf, gf = s.qf.to(dev), s.gf.to(dev)
+        plan = metrics.RankPlan(s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+        Q = qf.shape[0]
+        ms, r = timed(lambda: metrics.evaluate_features(qf, gf, plan=metrics.RankPlan(s.q_pids, s.g_pids, s.q_camids, s.g_camids),
+                                                        normalize=True))
+        res[key + "_eval"] = {"ms": ms, "queries_per_s": Q / ms * 1e3, "mAP": float(r.mAP)}
+
+        def rr():
+            dist = reranking.re_ranking_device(qf, gf, 20, 6, 0.3, normalize=True)
+            return metrics.evaluate_matrix(dist, plan=plan)
+        ms, r = timed(rr, iters=5)
+        res[key + "_rerank_k20_6"] = {"ms": ms, "queries_per_s": Q / ms * 1e3, "mAP": float(r.mAP)}
+    xs, labels = synth.make_triplet_batch()
+    xs = [x.to(dev).requires_grad_(True) for x in xs]
+    labels = labels.to(dev)
+    loss_fn = triplet_loss.TripletLoss()
+
+    def fwd():
+        return [loss_fn(x, labels)[0] for x in xs]
+
+    def fwd_bwd():
+        for x in xs:
+            x.grad = None
+        tot = sum(loss_fn(x, labels)[0] for x in xs)
+        tot.backward()
+        return tot
+    ms_f, _ = timed(fwd, iters=20)
+    ms_fb, _ = timed(fwd_bwd, iters=20)
+    res["triplet_3x128x768"] = {"fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "anchors_per_s_fwd": 384 / ms_f * 1e3}
+    return res
 
 
 def cpu_baseline(name, q_host, g_host, q_pid, g_pid, q_cam, g_cam):
@@ -341,6 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the small-workload timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -70,9 +70,10 @@ def cosine_similarity(qf, gf):
 # --------------------------------------------------------------------------
 # CMC / mAP
 # --------------------------------------------------------------------------
-def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50):
+def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50, sort_kind: str = "stable"):
     """Market-1501 protocol (utils/metrics.py:110-169) with the stable tie rule.
-    Returns (cmc float32[max_rank], mAP float64)."""
+    Returns (cmc float32[max_rank], mAP float64).  sort_kind=None reproduces the reference's
+    default (unstable) np.argsort -- used only to TIME the reference algorithm in bench.py."""
     distmat = np.asarray(distmat)
     q_pids, g_pids = np.asarray(q_pids), np.asarray(g_pids)
     q_camids, g_camids = np.asarray(q_camids), np.asarray(g_camids)
@@ -80,7 +81,7 @@ def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50):
     if num_g < max_rank:  # :118-120
         max_rank = num_g
         print("Note: number of gallery samples is quite small, got {}".format(num_g))
-    order_all = np.argsort(distmat, axis=1, kind="stable")  # :121
+    order_all = np.argsort(distmat, axis=1, kind=sort_kind)  # :121
     cmc_rows, aps = [], []
     for qi in range(num_q):
         order = order_all[qi]
