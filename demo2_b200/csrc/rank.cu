@@ -265,31 +265,30 @@ int launch_build_thresholds(const int* rec_ofs, const float* rec_dist, const int
 namespace {
 
 constexpr int kCmThreads = 256;
-constexpr int kCmWin = 63;
+constexpr int kCmWin = 2048;  // thresholds handled per pass over the row
 
 __global__ void __launch_bounds__(kCmThreads)
 count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
                     const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
                     const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
                     const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int window) {
-  extern __shared__ unsigned s_mem[];
-  float* s_thr = reinterpret_cast<float*>(s_mem);          // [64] (63 + pad)
-  int* s_tg = reinterpret_cast<int*>(s_mem + 64);          // [64]
-  unsigned* s_hist = s_mem + 128;                          // [kCmWin + 1][kCmThreads]
+  __shared__ float s_thr[kCmWin];
+  __shared__ int s_tg[kCmWin];
+  __shared__ unsigned s_hist[kCmWin + 8];
+  __shared__ unsigned s_warp[kCmThreads / 32];
   const int i = blockIdx.x;
   const int t = threadIdx.x;
   const int tbase = thr_ofs[i] + window * kCmWin;
   const int nthr = max(0, min(kCmWin, thr_cnt[i] - window * kCmWin));
   if (nthr == 0) return;
-  if (t < 64) {
-    s_thr[t] = t < nthr ? thr_val[tbase + t] : INFINITY;
-    s_tg[t] = t < nthr ? thr_gidx[tbase + t] : 0x7fffffff;
+  for (int k = t; k < nthr; k += kCmThreads) {
+    s_thr[k] = thr_val[tbase + k];
+    s_tg[k] = thr_gidx[tbase + k];
   }
-  for (int k = 0; k <= kCmWin; ++k) s_hist[k * kCmThreads + t] = 0u;
+  for (int k = t; k < kCmWin + 8; k += kCmThreads) s_hist[k] = 0u;
   __syncthreads();
   const float tmax = s_thr[nthr - 1];
   const float* row = distmat + static_cast<long long>(q_perm[i]) * ld;
-  unsigned* hist = s_hist + t;
   for (int g0 = 0; g0 < G; g0 += kCmThreads * 4) {
     float v[4];
 #pragma unroll
@@ -300,31 +299,43 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float d = v[u];
-      if (!(d <= tmax)) continue;  // beyond every threshold of the window (also skips padding)
-      int pos = 0;
-#pragma unroll
-      for (int step = 32; step >= 1; step >>= 1)
-        if (s_thr[pos + step - 1] <= d) pos += step;
+      if (!(d <= tmax)) continue;  // after every threshold of the window (also skips padding)
+      int lo = 0, hi = nthr;       // pos = #{thr <= d}
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_thr[mid] <= d) lo = mid + 1; else hi = mid;
+      }
+      int pos = lo;
       if (pos > 0 && s_thr[pos - 1] == d) {
         const int g = g_index_base + g0 + u * kCmThreads + t;
         while (pos > 0 && s_thr[pos - 1] == d && s_tg[pos - 1] > g) --pos;
       }
-      hist[pos * kCmThreads] += 1u;
+      atomicAdd(&s_hist[pos], 1u);
     }
   }
   __syncthreads();
-  // bucket totals, then prefix over buckets
-  __shared__ unsigned s_tot[kCmWin + 1];
-  if (t <= kCmWin) {
-    unsigned s = 0;
-    for (int k = 0; k < kCmThreads; ++k) s += s_hist[t * kCmThreads + ((k + t) & (kCmThreads - 1))];
-    s_tot[t] = s;
+  // counts[k] += sum_{b <= k} hist[b]: block-wide inclusive scan, 8 bins per thread
+  unsigned c[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    c[j] = s_hist[t * 8 + j];
+    sum += c[j];
   }
+  unsigned incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += x;
+  }
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
   __syncthreads();
-  if (t < nthr) {
-    unsigned run = 0;
-    for (int k = 0; k <= t; ++k) run += s_tot[k];
-    if (run) atomicAdd(counts + tbase + t, run);
+  unsigned run = incl - sum;
+  for (int w = 0; w < (t >> 5); ++w) run += s_warp[w];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    run += c[j];
+    const int k = t * 8 + j;
+    if (k < nthr && run) atomicAdd(counts + tbase + k, run);
   }
 }
 
@@ -334,16 +345,11 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
                         const int* thr_ofs, const int* thr_cnt, const float* thr_val, const int* thr_gidx,
                         unsigned* counts, int Q, int max_cnt, cudaStream_t stream) {
   if (Q <= 0 || G <= 0) return DEMO_OK;
-  const int smem = (128 + (kCmWin + 1) * kCmThreads) * 4;
-  static bool configured = false;
-  if (!configured) {
-    DEMO_CHECK_CUDA(cudaFuncSetAttribute(count_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static_assert(kCmWin == kCmThreads * 8, "scan layout");
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kCmWin);
   for (int w = 0; w < windows; ++w) {
-    count_matrix_kernel<<<Q, kCmThreads, smem, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
-                                                         thr_val, thr_gidx, counts, w);
+    count_matrix_kernel<<<Q, kCmThreads, 0, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
+                                                      thr_val, thr_gidx, counts, w);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
   return DEMO_OK;
@@ -354,28 +360,27 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
 // ---------------------------------------------------------------------------------------
 namespace {
 
-// per query: AP (float64) and rank of the first correct match
+// per query (one warp): AP (float64) and rank of the first correct match
 __global__ void query_ap_kernel(const int* __restrict__ thr_ofs, const int* __restrict__ thr_cnt,
                                 const int* __restrict__ thr_junk, const unsigned* __restrict__ counts,
                                 const int* __restrict__ q_perm, int Q, double* __restrict__ ap_out,
                                 int* __restrict__ first_out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= Q) return;
   const int s0 = thr_ofs[i], n = thr_cnt[i];
-  double ap = -1.0;
-  int first = 0;
-  if (n > 0) {
-    double acc = 0.0;
-    for (int j = 0; j < n; ++j) {
-      const int r = 1 + static_cast<int>(counts[s0 + j]) - thr_junk[s0 + j];
-      if (j == 0) first = r;
-      acc += static_cast<double>(j + 1) / static_cast<double>(r);
-    }
-    ap = acc / static_cast<double>(n);
+  double acc = 0.0;
+  for (int j = lane; j < n; j += 32) {
+    const int r = 1 + static_cast<int>(counts[s0 + j]) - thr_junk[s0 + j];
+    acc += static_cast<double>(j + 1) / static_cast<double>(r);
   }
-  const int q = q_perm[i];
-  ap_out[q] = ap;       // -1: query skipped (identity absent from the gallery)
-  first_out[q] = first; // 0: skipped
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const int q = q_perm[i];
+    ap_out[q] = n > 0 ? acc / static_cast<double>(n) : -1.0;  // -1: skipped (identity absent from the gallery)
+    first_out[q] = n > 0 ? 1 + static_cast<int>(counts[s0]) - thr_junk[s0] : 0;  // 0: skipped
+  }
 }
 
 // one block: deterministic reduction in original query order
@@ -426,7 +431,7 @@ int launch_finalize(const int* thr_ofs, const int* thr_cnt, const int* thr_junk,
                     int* num_valid_out, double* ap_out, int* first_out, double* scratch,
                     cudaStream_t stream) {
   DEMO_REQUIRE(max_rank > 0 && max_rank <= 4096, "finalize: max_rank out of range (%d)", max_rank);
-  query_ap_kernel<<<ceil_div(Q, 256), 256, 0, stream>>>(thr_ofs, thr_cnt, thr_junk, counts, q_perm, Q, ap_out,
+  query_ap_kernel<<<ceil_div(Q * 32, 256), 256, 0, stream>>>(thr_ofs, thr_cnt, thr_junk, counts, q_perm, Q, ap_out,
                                                         first_out);
   DEMO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned) * max_rank, stream));
   reduce_metrics_kernel<<<1, 1024, 0, stream>>>(ap_out, first_out, Q, max_rank, cmc_out, map_out, num_valid_out,

@@ -93,108 +93,186 @@ __global__ void transpose_add_kernel(const float* __restrict__ X, long long ldx,
 // ---------------------------------------------------------------------------------------
 constexpr int kTopkThreads = 256;
 
+constexpr int kTopkCap = 1024;  // candidate buffer of the fast path
+
+// block-wide bitonic sort of s[0..n2) ascending (n2 a power of two <= 1024), 256 threads
+__device__ void bitonic_sort_u64(unsigned long long* s, int n2) {
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += kTopkThreads) {
+        const int partner = i ^ stride;
+        if (partner > i) {
+          const bool up = (i & size) == 0;
+          const unsigned long long a = s[i], b = s[partner];
+          if ((a > b) == up) {
+            s[i] = b;
+            s[partner] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Fast path: the k-th smallest of the per-thread (or per-4-thread) minima is an upper bound T
+// of the k-th smallest entry of the row; the few entries <= T are collected and ranked by
+// (key, index).  Selection runs on the raw entries; the division by row_div (monotone) is
+// applied to the candidates only, after widening T over the entries whose quotient ties with
+// T's.  Fallback (more than kTopkCap candidates, i.e. massive ties): 4 x 8-bit radix select.
 template <bool kCached>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const float* __restrict__ row_div, int k,
                  int* __restrict__ idx_out, float* __restrict__ val_out) {
   extern __shared__ unsigned s_dyn[];
   __shared__ unsigned s_hist[256];
-  __shared__ unsigned s_prefix, s_need, s_nless, s_neq;
-  __shared__ unsigned long long s_cand[256];
-  unsigned* s_key = s_dyn;  // [cols] when cached
+  __shared__ unsigned s_prefix, s_need, s_nless, s_neq, s_ncand, s_bound;
+  __shared__ unsigned long long s_cand[kTopkCap];
+  unsigned* s_raw = s_dyn;  // [cols] raw ordered keys when cached
   const int row = blockIdx.x;
   const int t = threadIdx.x;
   const float* src = mat + (long long)row * ld;
   const float div = row_div ? row_div[row] : 1.f;
-  auto key_at = [&](int j) -> unsigned {
-    if (kCached) return s_key[j];
-    const float v = row_div ? src[j] / div : src[j];
-    return float_key(v + 0.f);
+  const bool has_div = row_div != nullptr;
+  auto raw_at = [&](int j) -> unsigned { return kCached ? s_raw[j] : float_key(__ldg(src + j) + 0.f); };
+  auto final_key = [&](unsigned raw) -> unsigned {  // ordering key: entry / row_div (canonical zero)
+    return has_div ? float_key(key_float(raw) / div + 0.f) : raw;
   };
-  if (kCached) {
-    for (int j = t; j < cols; j += kTopkThreads) {
-      const float v = row_div ? src[j] / div : src[j];
-      s_key[j] = float_key(v + 0.f);  // +0: canonical zero
+  auto key_at = [&](int j) -> unsigned { return final_key(raw_at(j)); };
+  unsigned tmin = 0xFFFFFFFFu;
+  // 8-byte vector loads when the row allows it (row start 8-byte aligned)
+  const bool vec2 = !kCached && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
+  const int cols2 = vec2 ? (cols >> 1) : 0;
+  if (vec2) {
+    const float2* src2 = reinterpret_cast<const float2*>(src);
+#pragma unroll 4
+    for (int j = t; j < cols2; j += kTopkThreads) {
+      const float2 v = __ldg(src2 + j);
+      tmin = min(tmin, min(float_key(v.x + 0.f), float_key(v.y + 0.f)));
     }
   }
-  if (t == 0) {
-    s_prefix = 0;
-    s_need = k;
+  for (int j = 2 * cols2 + t; j < cols; j += kTopkThreads) {
+    const unsigned raw = float_key(__ldg(src + j) + 0.f);
+    if (kCached) s_raw[j] = raw;
+    tmin = min(tmin, raw);
   }
+  unsigned* s_min = s_hist;  // reuse: [256]
+  s_min[t] = tmin;
+  if (t == 0) s_ncand = 0;
   __syncthreads();
-  // 4 x 8-bit radix select for the k-th smallest key
-  for (int pass = 3; pass >= 0; --pass) {
-    s_hist[t] = 0;
-    __syncthreads();
-    const unsigned prefix = s_prefix;
-    const unsigned hi_mask = pass == 3 ? 0u : (0xFFFFFFFFu << ((pass + 1) * 8));
-    for (int j = t; j < cols; j += kTopkThreads) {
-      const unsigned key = key_at(j);
-      if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(key >> (pass * 8)) & 255u], 1u);
+  // bound = k-th smallest of M group minima (M = 64 groups of 4 threads when k <= 64, else 256)
+  const int M = k <= 64 ? 64 : 256;
+  unsigned mine = 0xFFFFFFFFu;
+  if (t < M) mine = M == 64 ? min(min(s_min[4 * t], s_min[4 * t + 1]), min(s_min[4 * t + 2], s_min[4 * t + 3])) : s_min[t];
+  __syncthreads();
+  if (t < M) s_min[t] = mine;
+  __syncthreads();
+  if (t < M) {
+    int rank = 0;
+    for (int u = 0; u < M; ++u) {
+      const unsigned o = s_min[u];
+      rank += (o < mine || (o == mine && u < t)) ? 1 : 0;
     }
-    __syncthreads();
-    if (t == 0) {
-      unsigned need = s_need, cum = 0;
-      int b = 0;
-      for (; b < 256; ++b) {
-        if (cum + s_hist[b] >= need) break;
-        cum += s_hist[b];
+    if (rank == min(k, M) - 1) {
+      unsigned bound = mine;
+      if (has_div && bound < 0xFF000000u) {
+        // widen over raw values whose quotient equals the bound's quotient
+        const unsigned qb = final_key(bound);
+        for (int it = 0; it < 8 && final_key(bound + 1u) == qb; ++it) ++bound;
       }
-      s_need = need - cum;
-      s_prefix = prefix | (static_cast<unsigned>(b) << (pass * 8));
+      s_bound = bound;
     }
-    __syncthreads();
-  }
-  const unsigned kth = s_prefix;
-  const unsigned take_eq = s_need;  // how many of the keys == kth belong to the top-k (lowest indices)
-  if (t == 0) {
-    s_nless = 0;
-    s_neq = 0;
   }
   __syncthreads();
-  // keys < kth: any order (sorted below); keys == kth: first `take_eq` in index order
-  for (int j0 = 0; j0 < cols; j0 += kTopkThreads) {
-    const int j = j0 + t;
-    const unsigned key = j < cols ? key_at(j) : 0xFFFFFFFFu;
-    if (j < cols && key < kth) {
-      const unsigned p = atomicAdd(&s_nless, 1u);
-      s_cand[p] = (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned>(j);
+  const unsigned bound = s_bound;
+  auto offer = [&](unsigned raw, int j) {
+    if (raw <= bound) {
+      const unsigned p = atomicAdd(&s_ncand, 1u);
+      if (p < kTopkCap) s_cand[p] = (static_cast<unsigned long long>(final_key(raw)) << 32) | static_cast<unsigned>(j);
     }
-    // ordered compaction of the ties
-    const bool eq = j < cols && key == kth;
-    const unsigned ball = __ballot_sync(0xffffffffu, eq);
-    __shared__ unsigned s_wcnt[kTopkThreads / 32];
-    if ((t & 31) == 0) s_wcnt[t >> 5] = __popc(ball);
+  };
+  if (vec2) {
+    const float2* src2 = reinterpret_cast<const float2*>(src);
+#pragma unroll 4
+    for (int j = t; j < cols2; j += kTopkThreads) {
+      const float2 v = __ldg(src2 + j);
+      offer(float_key(v.x + 0.f), 2 * j);
+      offer(float_key(v.y + 0.f), 2 * j + 1);
+    }
+  }
+  for (int j = 2 * cols2 + t; j < cols; j += kTopkThreads) offer(raw_at(j), j);
+  __syncthreads();
+  const unsigned ncand = s_ncand;
+  if (ncand <= 256) {
+    // rank by counting: candidate i goes to position #{candidates smaller}
+    unsigned long long me = ~0ull;
+    int pos = 0;
+    if (t < static_cast<int>(ncand)) {
+      me = s_cand[t];
+      for (unsigned u = 0; u < ncand; ++u) pos += s_cand[u] < me ? 1 : 0;
+    }
     __syncthreads();
-    unsigned before = s_neq;
-    for (int w = 0; w < (t >> 5); ++w) before += s_wcnt[w];
-    before += __popc(ball & ((1u << (t & 31)) - 1u));
-    if (eq && before < take_eq)
-      s_cand[(k - take_eq) + before] = (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned>(j);
+    if (t < static_cast<int>(ncand)) s_cand[pos] = me;
     __syncthreads();
+  } else
+  if (ncand <= kTopkCap) {
+    int n2 = 32;
+    while (n2 < static_cast<int>(ncand)) n2 <<= 1;
+    for (int i = ncand + t; i < n2; i += kTopkThreads) s_cand[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(s_cand, n2);
+  } else {
+    // ---- fallback: radix select ----
     if (t == 0) {
-      unsigned tot = 0;
-      for (int w = 0; w < kTopkThreads / 32; ++w) tot += s_wcnt[w];
-      s_neq += tot;
+      s_prefix = 0;
+      s_need = k;
+      s_nless = 0;
+      s_neq = 0;
     }
     __syncthreads();
-  }
-  // bitonic sort of the k candidates (padded to 256) by (key, index)
-  if (t >= k) s_cand[t] = ~0ull;
-  __syncthreads();
-  for (int size = 2; size <= 256; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const int partner = t ^ stride;
-      if (partner > t) {
-        const bool up = (t & size) == 0;
-        const unsigned long long a = s_cand[t], b = s_cand[partner];
-        if ((a > b) == up) {
-          s_cand[t] = b;
-          s_cand[partner] = a;
+    for (int pass = 3; pass >= 0; --pass) {
+      s_hist[t] = 0;
+      __syncthreads();
+      const unsigned prefix = s_prefix;
+      const unsigned hi_mask = pass == 3 ? 0u : (0xFFFFFFFFu << ((pass + 1) * 8));
+      for (int j = t; j < cols; j += kTopkThreads) {
+        const unsigned key = key_at(j);
+        if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(key >> (pass * 8)) & 255u], 1u);
+      }
+      __syncthreads();
+      if (t == 0) {
+        unsigned need = s_need, cum = 0;
+        int bin = 0;
+        for (; bin < 256; ++bin) {
+          if (cum + s_hist[bin] >= need) break;
+          cum += s_hist[bin];
         }
+        s_need = need - cum;
+        s_prefix = prefix | (static_cast<unsigned>(bin) << (pass * 8));
       }
       __syncthreads();
     }
+    const unsigned kth = s_prefix;
+    const unsigned take_eq = s_need;  // how many keys == kth belong to the top-k (lowest columns)
+    for (int j = t; j < cols; j += kTopkThreads) {
+      const unsigned key = key_at(j);
+      if (key < kth) {
+        const unsigned p = atomicAdd(&s_nless, 1u);
+        s_cand[p] = (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned>(j);
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned got = 0;
+      for (int j = 0; j < cols && got < take_eq; ++j)
+        if (key_at(j) == kth) s_cand[(k - take_eq) + got++] = (static_cast<unsigned long long>(kth) << 32) | static_cast<unsigned>(j);
+    }
+    __syncthreads();
+    int n2 = 32;
+    while (n2 < k) n2 <<= 1;
+    for (int i = k + t; i < n2; i += kTopkThreads) s_cand[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(s_cand, n2);
   }
   if (t < k) {
     const unsigned long long c = s_cand[t];
@@ -463,8 +541,10 @@ int launch_topk_rows(const float* mat, long long ld, int rows, int cols, const f
                      float* val_out, cudaStream_t stream) {
   DEMO_REQUIRE(k >= 1 && k <= 256 && k <= cols, "topk: k=%d out of range (cols=%d, max 256)", k, cols);
   if (rows <= 0) return DEMO_OK;
+  // Long rows are not staged in shared memory: the second (filter) pass re-reads them from L2,
+  // which keeps 8 blocks resident per SM instead of 4 and hides the load latency better.
   const size_t smem = static_cast<size_t>(cols) * 4;
-  if (smem <= 200 * 1024) {
+  if (smem <= 16 * 1024) {
     static bool configured = false;
     if (!configured) {
       DEMO_CHECK_CUDA(cudaFuncSetAttribute(topk_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
