@@ -1,4 +1,6 @@
 // extern "C" entry points for the rank-count evaluation (include/demo_b200.h).
+#include <cstdlib>
+
 #include "gemm_epilogues.cuh"
 #include "rank.cuh"
 
@@ -107,8 +109,9 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
   }
   const Schedule s = make_chunked_schedule(Q, G, chunk_tiles);
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kWin);
+  static const bool no_epi = getenv("DEMO_DEBUG_NOEPI") != nullptr;  // timing experiments only
   for (int wdw = 0; wdw < windows; ++wdw) {
-    ep.window = wdw;
+    ep.window = no_epi ? -1 : wdw;
     DEMO_TRY(launch_sqdist_gemm<EpiCount>(ops, s, s.num_units, ep, stream));
   }
   return DEMO_OK;

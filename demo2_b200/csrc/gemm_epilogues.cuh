@@ -41,15 +41,20 @@ struct EpiColumns {
     s_col = reinterpret_cast<float2*>(smem);
     s_lab = reinterpret_cast<int*>(smem + 2 * kBN * 8);
   }
-  __device__ __forceinline__ void stage(const TileInfo& t, int as, int epi_tid, const float* b_norm,
-                                        const float* b_inv, const int* b_lab) {
-    for (int c = epi_tid; c < kBN; c += kEpiThreads) {
-      const bool ok = c < t.n_valid;
-      s_col[as * kBN + c] = make_float2(ok ? -2.f * __ldg(b_inv + t.n0 + c) : 0.f,
-                                        ok ? __ldg(b_norm + t.n0 + c) : INFINITY);
-      if (b_lab) s_lab[as * kBN + c] = ok ? __ldg(b_lab + t.n0 + c) : -0x7fffffff;
-    }
-    epi_bar_sync();
+  // one column per epilogue thread (kEpiThreads == kBN): global -> registers ...
+  float2 r_col;
+  int r_lab;
+  __device__ __forceinline__ void load(const TileInfo& t, int epi_tid, const float* b_norm, const float* b_inv,
+                                       const int* b_lab, float invalid_norm) {
+    const bool ok = epi_tid < t.n_valid;
+    r_col = make_float2(ok ? -2.f * __ldg(b_inv + t.n0 + epi_tid) : 0.f,
+                        ok ? __ldg(b_norm + t.n0 + epi_tid) : invalid_norm);
+    r_lab = (b_lab && ok) ? __ldg(b_lab + t.n0 + epi_tid) : -0x7fffffff;
+  }
+  // ... -> shared memory buffer `as` (made visible by the barrier at the next tile_begin)
+  __device__ __forceinline__ void store(int as, int epi_tid) {
+    s_col[as * kBN + epi_tid] = r_col;
+    s_lab[as * kBN + epi_tid] = r_lab;
   }
 };
 
@@ -77,9 +82,9 @@ struct EpiStore {
   __device__ EpiStore(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
       : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {}
 
-  __device__ void tile_begin(const TileInfo& t, int as) {
-    cols.stage(t, as, epi_tid, p.b_norm, p.b_inv, nullptr);
-  }
+  __device__ void stage_load(const TileInfo& t) { cols.load(t, epi_tid, p.b_norm, p.b_inv, nullptr, INFINITY); }
+  __device__ void stage_store(int as) { cols.store(as, epi_tid); }
+  __device__ void tile_begin(const TileInfo&, int) { epi_bar_sync(); }
   __device__ void tile_body(const TileInfo& t, int as, uint32_t taddr) {
     const int row = t.m0 + row_in_tile;
     const bool row_ok = row < p.M;
@@ -147,11 +152,12 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
   asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(kOff));  // not volatile: free to schedule
   return v;
 }
+template <int kOff>
 __device__ __forceinline__ void hist_inc_u16(uint32_t addr) {  // ordered read-modify-write
   uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(kOff));
   v += 1u;
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v));
+  asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(addr), "n"(kOff), "r"(v));
 }
 
 struct EpiCount {
@@ -178,8 +184,9 @@ struct EpiCount {
   float* s_thr;               // [kWin][128]     column = row_in_tile (shared by both column halves)
   unsigned short* s_hist;     // [kWin+1][256]   column = epi_tid (private)
   int epi_tid, row_in_tile, col0;
-  int hcol;                   // histogram column: warps 2m / 2m+1 share 32-bit words (low / high half) so
-                              // that the 32 lanes of one warp hit 32 different banks
+  int hcol;                   // histogram column 2*row + half: the two column halves of a row share a 32-bit
+                              // word (low / high u16), so counter b sits at a CONSTANT byte offset
+                              // (kWin*512 + 2*half) from threshold b and a warp hits 32 different banks
   int nthr = 0, tbase = 0;
   // top three levels of the search tree live in registers
   float t31 = 0, t15 = 0, t47 = 0, t7 = 0, t23 = 0, t39 = 0, t55 = 0;
@@ -189,32 +196,39 @@ struct EpiCount {
     s_col = reinterpret_cast<float2*>(smem);
     s_thr = reinterpret_cast<float*>(smem + 2 * kBN * 8);
     s_hist = reinterpret_cast<unsigned short*>(smem + 2 * kBN * 8 + kWin * kRowBytes);
-    hcol = (((epi_tid >> 6) * 32 + (epi_tid & 31)) << 1) | ((epi_tid >> 5) & 1);
+    hcol = (row_in_tile << 1) | (col0 ? 1 : 0);
   }
 
+  float2 r_col;
+  float na = 0.f, ia = 0.f;   // per-row constants of the current unit
+  __device__ void stage_load(const TileInfo& t) {
+    const bool ok = epi_tid < t.n_valid;
+    // invalid columns get a huge FINITE distance: they land in the (unused) bucket after the
+    // last real threshold and can never tie with the +inf padding
+    r_col = make_float2(ok ? -2.f * __ldg(p.b_inv + t.n0 + epi_tid) : 0.f,
+                        ok ? __ldg(p.b_norm + t.n0 + epi_tid) : 3.0e38f);
+  }
+  __device__ void stage_store(int as) { s_col[as * kBN + epi_tid] = r_col; }
+
   __device__ void tile_begin(const TileInfo& t, int as) {
+    // everybody has left the previous tile body (s_thr is shared by the two warps of a lane
+    // quadrant) and the staged columns of this tile are visible
+    epi_bar_sync();
     if (t.first_in_unit) {
-      // s_thr is shared by the two warps of a lane quadrant: the partner may still be searching
-      // the previous unit's thresholds, so everybody must have left that tile body first
-      epi_bar_sync();
       const int row = t.m0 + row_in_tile;
       nthr = 0;
+      na = ia = 0.f;
       if (row < p.M) {
         tbase = __ldg(p.thr_ofs + row) + p.window * kWin;
         nthr = max(0, min(kWin, __ldg(p.thr_cnt + row) - p.window * kWin));
+        na = __ldg(p.a_norm + row);
+        ia = __ldg(p.a_inv + row);
       }
       // the two threads of a row (column halves) fill alternate threshold slots
       for (int k = (col0 ? 1 : 0); k < kWin; k += 2)
         s_thr[k * 128 + row_in_tile] = k < nthr ? __ldg(p.thr_val + tbase + k) : INFINITY;
       for (int k = 0; k <= kWin; ++k) s_hist[k * kEpiThreads + hcol] = 0;
-    }
-    for (int c = epi_tid; c < kBN; c += kEpiThreads) {
-      const bool ok = c < t.n_valid;
-      s_col[as * kBN + c] = make_float2(ok ? -2.f * __ldg(p.b_inv + t.n0 + c) : 0.f,
-                                        ok ? __ldg(p.b_norm + t.n0 + c) : INFINITY);
-    }
-    epi_bar_sync();
-    if (t.first_in_unit) {
+      epi_bar_sync();
       const float* thr = s_thr + row_in_tile;
       t31 = thr[31 * 128];
       t15 = thr[15 * 128];
@@ -237,13 +251,17 @@ struct EpiCount {
   }
 
   __device__ void tile_body(const TileInfo& t, int as, uint32_t taddr) {
+    if (col0) tile_body_half<1>(t, as, taddr); else tile_body_half<0>(t, as, taddr);  // warp-uniform
+  }
+
+  template <int kHalf>
+  __device__ __forceinline__ void tile_body_half(const TileInfo& t, int as, uint32_t taddr) {
+    constexpr int kHistOff = kWin * kRowBytes + 2 * kHalf;
     const int row = t.m0 + row_in_tile;
     const bool active = nthr > 0;
+    if (p.window < 0) return;  // debug: mainloop-only timing (DEMO_DEBUG_NOEPI)
     if (!__any_sync(0xffffffffu, active)) return;  // whole warp beyond M / without positives
-    const float na = active ? __ldg(p.a_norm + row) : 0.f;
-    const float ia = active ? __ldg(p.a_inv + row) : 0.f;
     const uint32_t thr0 = smem_u32(s_thr + row_in_tile);             // bucket b at thr0 + b*512
-    const uint32_t hist_delta = smem_u32(s_hist + hcol) - thr0;   // counter b at thr0 + delta + b*512
     const float2* col = s_col + as * kBN + col0;
     const int n_here = t.n_valid - col0;
     constexpr int kC = 16;
@@ -286,7 +304,7 @@ struct EpiCount {
         q = u <= d;
         a += q ? 1 * kRowBytes : 0;
         last = q ? u : last;
-        ties |= (last == d && d < INFINITY) ? (1u << j) : 0u;
+        ties |= (last == d) ? (1u << j) : 0u;
         slot[j] = a;
       }
       if (ties && active) {
@@ -301,7 +319,7 @@ struct EpiCount {
         }
       }
 #pragma unroll
-      for (int j = 0; j < kC; ++j) hist_inc_u16(slot[j] + hist_delta);
+      for (int j = 0; j < kC; ++j) hist_inc_u16<kHistOff>(slot[j]);
     }
   }
 
@@ -343,9 +361,9 @@ struct EpiExtract {
   __device__ EpiExtract(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
       : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {}
 
-  __device__ void tile_begin(const TileInfo& t, int as) {
-    cols.stage(t, as, epi_tid, p.b_norm, p.b_inv, p.b_pid);
-  }
+  __device__ void stage_load(const TileInfo& t) { cols.load(t, epi_tid, p.b_norm, p.b_inv, p.b_pid, INFINITY); }
+  __device__ void stage_store(int as) { cols.store(as, epi_tid); }
+  __device__ void tile_begin(const TileInfo&, int) { epi_bar_sync(); }
   __device__ void tile_body(const TileInfo& t, int as, uint32_t taddr) {
     const int row = t.m0 + row_in_tile;
     const bool row_ok = row < p.M;
@@ -406,9 +424,9 @@ struct EpiMine {
   __device__ EpiMine(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
       : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {}
 
-  __device__ void tile_begin(const TileInfo& t, int as) {
-    cols.stage(t, as, epi_tid, p.b_norm, p.b_inv, p.b_lab);
-  }
+  __device__ void stage_load(const TileInfo& t) { cols.load(t, epi_tid, p.b_norm, p.b_inv, p.b_lab, INFINITY); }
+  __device__ void stage_store(int as) { cols.store(as, epi_tid); }
+  __device__ void tile_begin(const TileInfo&, int) { epi_bar_sync(); }
   __device__ void tile_body(const TileInfo& t, int as, uint32_t taddr) {
     const int row = t.m0 + row_in_tile;
     const bool row_ok = row < p.M;

@@ -91,6 +91,52 @@ struct TileInfo {
   bool first_in_unit, last_in_unit;
 };
 
+// Walks the tiles of a CTA in schedule order (same order as the producer / MMA loops).
+struct TileCursor {
+  const Schedule& s;
+  int num_units, u, stride, n_off;
+  WorkUnit w;
+  __device__ TileCursor(const Schedule& s_, int num_units_, int first, int stride_)
+      : s(s_), num_units(num_units_), u(first), stride(stride_), n_off(0) {
+    skip_empty();
+  }
+  __device__ TileCursor& operator=(const TileCursor& o) {
+    num_units = o.num_units;
+    u = o.u;
+    stride = o.stride;
+    n_off = o.n_off;
+    w = o.w;
+    return *this;
+  }
+  __device__ TileCursor(const TileCursor& o) = default;
+  __device__ void skip_empty() {
+    while (u < num_units) {
+      w = schedule_get(s, u);
+      if (w.n_rows > 0) break;
+      u += stride;
+    }
+  }
+  __device__ bool valid() const { return u < num_units; }
+  __device__ void advance() {
+    n_off += kBN;
+    if (n_off >= w.n_rows) {
+      n_off = 0;
+      u += stride;
+      skip_empty();
+    }
+  }
+  __device__ TileInfo info() const {
+    TileInfo t;
+    t.m0 = w.m0;
+    t.n0 = w.n0 + n_off;
+    t.n_valid = min(kBN, w.n_rows - n_off);
+    t.unit_index = u;
+    t.first_in_unit = n_off == 0;
+    t.last_in_unit = n_off + kBN >= w.n_rows;
+    return t;
+  }
+};
+
 template <class Epi>
 struct GemmSmem {
   static constexpr int kStages = Epi::kStages;
@@ -222,30 +268,34 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     Epi epi(ep, epi_smem, epi_tid, row_in_tile, col0);
     int as = 0;
     uint32_t aphase = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-      const WorkUnit w = schedule_get(sched, u);
-      for (int n_off = 0; n_off < w.n_rows; n_off += kBN) {
-        TileInfo t;
-        t.m0 = w.m0;
-        t.n0 = w.n0 + n_off;
-        t.n_valid = min(kBN, w.n_rows - n_off);
-        t.unit_index = u;
-        t.first_in_unit = n_off == 0;
-        t.last_in_unit = n_off + kBN >= w.n_rows;
-        epi.tile_begin(t, as);  // may stage per-column metadata (overlaps the MMAs)
-        mbar_wait(&bar_tfull[as], aphase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(as * kBN + col0);
-        epi.tile_body(t, as, taddr);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tempty[as]);
-        epi.tile_end(t, as);
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1u;
-        }
+    // The per-column metadata of tile i+1 is fetched from global memory while tile i is being
+    // processed (stage_load -> registers, stage_store -> the other shared-memory buffer), so its
+    // L2 latency never sits between two tiles.
+    TileCursor cur(sched, num_units, blockIdx.x, gridDim.x);
+    if (cur.valid()) {
+      epi.stage_load(cur.info());
+      epi.stage_store(0);
+    }
+    while (cur.valid()) {
+      const TileInfo t = cur.info();
+      TileCursor nxt = cur;
+      nxt.advance();
+      epi.tile_begin(t, as);  // starts with an epilogue-wide barrier: staged columns become visible
+      if (nxt.valid()) epi.stage_load(nxt.info());
+      mbar_wait(&bar_tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(as * kBN + col0);
+      epi.tile_body(t, as, taddr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[as]);
+      epi.tile_end(t, as);
+      if (nxt.valid()) epi.stage_store(as ^ 1);
+      cur = nxt;
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
       }
     }
   }
