@@ -246,6 +246,19 @@ def evaluate_matrix(distmat, q_pids=None, g_pids=None, q_camids=None, g_camids=N
     return EvalResult(cmc, mAP, nvalid, w.view("ap", torch.float64, Q), w.view("first", torch.int32, Q))
 
 
+def evaluate_auto(qf, gf, q_pids=None, g_pids=None, q_camids=None, g_camids=None, max_rank: int = 50,
+                  normalize: bool = False, plan: RankPlan | None = None) -> EvalResult:
+    """What R1_mAP_eval.compute does without re-ranking: materialise the matrix when it is small
+    (one GEMM + one streaming count pass; best when queries have hundreds of positives), fused
+    rank-count GEMM epilogue otherwise (Q x G never written)."""
+    q, g = _features(qf), _features(gf)
+    if plan is None:
+        plan = RankPlan(q_pids, g_pids, q_camids, g_camids)
+    if q.shape[0] * g.shape[0] <= MAX_MATERIALIZE:
+        return evaluate_matrix(sqdist_device(q, g, _lib.DIST_SQ, normalize=normalize), plan=plan, max_rank=max_rank)
+    return evaluate_features(q, g, plan=plan, normalize=normalize, max_rank=max_rank)
+
+
 def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=50):
     """utils/metrics.py:110-169 -- Market-1501 CMC / mAP.  Ties are broken by ascending gallery
     index (the reference's np.argsort leaves tie order unspecified)."""
