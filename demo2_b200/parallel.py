@@ -194,3 +194,40 @@ class ShardedEvaluator:
                            "count": (t4, t5), "allreduce": (t5, t6), "finalize": (t6, t7)})
             timers["launches"] = eng.launches(max(1, -(-max_cnt // 63)))
         return EvalResult(cmc, mAP, nvalid, ap, first)
+
+
+def evaluate_gallery_chunks(qf, gf, q_pid, g_pid, q_cam, g_cam, n_chunks: int, normalize: bool = False,
+                            max_rank: int = 50, engine=None):
+    """The sharded algorithm with all "ranks" executed one after another on ONE device: the
+    gallery is cut into `n_chunks` contiguous chunks, every chunk contributes its records, the
+    merged thresholds are counted against every chunk and the counts simply add up.  Result is
+    bit-identical to the unsharded evaluation (rank counts are additive over gallery partitions);
+    used to test the multi-GPU data flow on a single GPU and to evaluate galleries chunk-wise."""
+    from .metrics import EvalResult
+    eng = engine if engine is not None else CudaEngine()
+    G = len(g_pid)
+    plans, works, recs_l, cnts = [], [], [], []
+    for c in range(n_chunks):
+        lo, hi = shard_range(G, n_chunks, c)
+        plan = eng.plan(q_pid, g_pid[lo:hi], q_cam, g_cam[lo:hi])
+        w, recs = eng.records(plan, qf, gf[lo:hi], lo, normalize)
+        plans.append(plan)
+        works.append(w)
+        recs_l.append(recs)
+        cnts.append((plan.rec_ofs[1:] - plan.rec_ofs[:-1]).to(torch.int32))
+    t_max = max(max(int(r.shape[1]) for r in recs_l), 1)
+    padded = torch.zeros((n_chunks, 3, t_max), dtype=torch.int32, device=recs_l[0].device)
+    for c, r in enumerate(recs_l):
+        padded[c, :, :r.shape[1]] = r
+    thr_ofs, merged, T, max_cnt = merge_records(torch.stack(cnts), padded)
+    Q = plans[0].Q
+    thr_cnt, thr_val, thr_gidx, thr_junk = eng.thresholds(thr_ofs, merged, Q)
+    counts = torch.zeros(max(T, 1), dtype=torch.int32, device=merged.device)
+    if T > 0:
+        for plan, w in zip(plans, works):
+            eng.count(w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt)
+    cmc_d, scal_d, ap, first = eng.finalize(thr_ofs, thr_cnt, thr_junk, counts, plans[0].q_perm, Q,
+                                            min(max_rank, G))
+    scal = scal_d.cpu()
+    return EvalResult(cmc_d.cpu().numpy(), np.float64(scal[0].item()), int(scal[1:2].view(torch.int32)[0].item()),
+                      ap, first)
