@@ -99,6 +99,7 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
   ep.thr_gidx = thr_gidx;
   ep.counts = counts;
   ep.M = Q;
+  ep.dbg = nullptr;
   if (chunk_tiles <= 0) {
     // enough units to balance 148 persistent CTAs (>= ~8 units each) but long enough to
     // amortise the per-unit threshold load / histogram flush
@@ -112,6 +113,31 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
   static const bool no_epi = getenv("DEMO_DEBUG_NOEPI") != nullptr;  // timing experiments only
   for (int wdw = 0; wdw < windows; ++wdw) {
     ep.window = no_epi ? -1 : wdw;
+    static const int dbg = getenv("DEMO_DEBUG_EPI") ? atoi(getenv("DEMO_DEBUG_EPI")) : 0;
+    if (dbg == 1) { DEMO_TRY(launch_sqdist_gemm<EpiCountT<1>>(ops, s, s.num_units, *reinterpret_cast<EpiCountT<1>::Params*>(&ep), stream)); continue; }
+    if (dbg == 2) { DEMO_TRY(launch_sqdist_gemm<EpiCountT<2>>(ops, s, s.num_units, *reinterpret_cast<EpiCountT<2>::Params*>(&ep), stream)); continue; }
+    if (dbg == 3) { DEMO_TRY(launch_sqdist_gemm<EpiCountT<3>>(ops, s, s.num_units, *reinterpret_cast<EpiCountT<3>::Params*>(&ep), stream)); continue; }
+    if (dbg == 4) {
+      static unsigned long long* dptr = nullptr;
+      if (!dptr) cudaMalloc(&dptr, 64);
+      cudaMemsetAsync(dptr, 0, 64, stream);
+      ep.dbg = dptr;
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, stream);
+      DEMO_TRY(launch_sqdist_gemm<EpiCountT<4>>(ops, s, s.num_units, *reinterpret_cast<EpiCountT<4>::Params*>(&ep), stream));
+      cudaEventRecord(e1, stream);
+      unsigned long long h[6];
+      cudaMemcpyAsync(h, dptr, 48, cudaMemcpyDeviceToHost, stream);
+      cudaStreamSynchronize(stream);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double warps = 8.0 * (s.num_units < num_sms() ? s.num_units : num_sms());
+      printf("[prof] %.2f ms | per epilogue warp, Mcycles: tfull-wait %.1f  tmem-ld %.1f  bisect %.1f  hist %.1f  tile_begin %.1f | chunks/warp %.0f\n",
+             ms, h[0] / warps * 1e-6, h[1] / warps * 1e-6, h[2] / warps * 1e-6, h[3] / warps * 1e-6, h[4] / warps * 1e-6, h[5] / warps);
+      continue;
+    }
     DEMO_TRY(launch_sqdist_gemm<EpiCount>(ops, s, s.num_units, ep, stream));
   }
   return DEMO_OK;

@@ -62,6 +62,7 @@ struct EpiColumns {
 // STORE: materialise the matrix (euclidean_distance, cosine_*, re-ranking all-pairs)
 // ---------------------------------------------------------------------------------------
 struct EpiStore {
+  static constexpr bool kProfile = false;
   static constexpr int kStages = 4;
   static constexpr int kSmemBytes = EpiColumns::kBytes;
   struct Params {
@@ -160,7 +161,10 @@ __device__ __forceinline__ void hist_inc_u16(uint32_t addr) {  // ordered read-m
   asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(addr), "n"(kOff), "r"(v));
 }
 
-struct EpiCount {
+template <int kDbg>
+struct EpiCountT {
+  static constexpr bool kProfile = kDbg == 4;
+  unsigned prof[6] = {0, 0, 0, 0, 0, 0};  // cycles: tfull wait | tmem ld | bisect | hist | tile_begin | chunks
   static constexpr int kStages = 3;
   static constexpr int kRowBytes = 512;  // one bucket row: 128 x f32 thresholds == 256 x u16 counters
   // columns x2 buffers | thresholds [kWin][128] f32 | histogram [kWin+1][256] u16
@@ -178,6 +182,7 @@ struct EpiCount {
     unsigned* counts;         // += #{gallery columns lexicographically before the threshold}
     int M;
     int window;               // thresholds [window*kWin, window*kWin + kWin) of every row
+    unsigned long long* dbg;  // profiling variant only
   };
   const Params& p;
   float2* s_col;              // [2][kBN]
@@ -191,7 +196,7 @@ struct EpiCount {
   // top three levels of the search tree live in registers
   float t31 = 0, t15 = 0, t47 = 0, t7 = 0, t23 = 0, t39 = 0, t55 = 0;
 
-  __device__ EpiCount(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
+  __device__ EpiCountT(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
       : p(p_), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {
     s_col = reinterpret_cast<float2*>(smem);
     s_thr = reinterpret_cast<float*>(smem + 2 * kBN * 8);
@@ -270,8 +275,11 @@ struct EpiCount {
       if (c * kC >= n_here) break;  // warp-uniform
       uint32_t r[kC];
       __syncwarp();
+      unsigned c0 = 0, c1 = 0, c2 = 0;
+      if (kDbg == 4) c0 = clock();
       tmem_ld_32x16(taddr + c * kC, r);
       tmem_ld_wait();
+      if (kDbg == 4) c1 = clock();
       uint32_t slot[kC];   // shared address of the threshold row == bucket, per element
       uint32_t ties = 0;
 #pragma unroll
@@ -291,6 +299,7 @@ struct EpiCount {
         const bool p3 = u3 <= d;
         a += p3 ? 8 * kRowBytes : 0;
         last = p3 ? u3 : last;
+        if (kDbg == 2 || kDbg == 3) { slot[j] = a + (kDbg == 3 ? (__float_as_uint(d) & 4u) : 0u); continue; }
         // level 4..6 from shared memory (immediate offsets, one predicated add per level)
         float u = lds_f32_off<3 * kRowBytes>(a);
         bool q = u <= d;
@@ -318,8 +327,29 @@ struct EpiCount {
           }
         }
       }
+      if (kDbg == 4) {
+        uint32_t x = 0;
 #pragma unroll
-      for (int j = 0; j < kC; ++j) hist_inc_u16<kHistOff>(slot[j]);
+        for (int j = 0; j < kC; ++j) x ^= slot[j];
+        if (x == 0x12345u) prof[5] += 1000;   // forces the slots to be complete here
+        c2 = clock();
+      }
+      if (kDbg == 1 || kDbg == 3) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < kC; ++j) x ^= slot[j];
+        if (x == 0x12345u) hist_inc_u16<kHistOff>(thr0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kC; ++j) hist_inc_u16<kHistOff>(slot[j]);
+      }
+      if (kDbg == 4) {
+        const unsigned c3 = clock();
+        prof[1] += c1 - c0;
+        prof[2] += c2 - c1;
+        prof[3] += c3 - c2;
+        prof[5] += 1;
+      }
     }
   }
 
@@ -334,12 +364,15 @@ struct EpiCount {
   }
 };
 
+using EpiCount = EpiCountT<0>;
+
 // ---------------------------------------------------------------------------------------
 // EXTRACT: distances of the same-identity pairs (positives + junk) of every query.
 // Gallery rows are sorted by pid, so the candidates of query q are the contiguous rows
 // [g_lo[q], g_lo[q] + cnt[q]) and the record slot is rec_base[q] + (row - g_lo[q]).
 // ---------------------------------------------------------------------------------------
 struct EpiExtract {
+  static constexpr bool kProfile = false;
   static constexpr int kStages = 4;
   static constexpr int kSmemBytes = EpiColumns::kBytes;
   struct Params {
@@ -404,6 +437,7 @@ struct EpiExtract {
 // (ordered distance key << 32 | index code).
 // ---------------------------------------------------------------------------------------
 struct EpiMine {
+  static constexpr bool kProfile = false;
   static constexpr int kStages = 4;
   static constexpr int kSmemBytes = EpiColumns::kBytes;
   struct Params {

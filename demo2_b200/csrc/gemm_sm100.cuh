@@ -280,10 +280,17 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const TileInfo t = cur.info();
       TileCursor nxt = cur;
       nxt.advance();
+      unsigned pc0 = 0, pc1 = 0;
+      if constexpr (Epi::kProfile) pc0 = clock();
       epi.tile_begin(t, as);  // starts with an epilogue-wide barrier: staged columns become visible
       if (nxt.valid()) epi.stage_load(nxt.info());
+      if constexpr (Epi::kProfile) pc1 = clock();
       mbar_wait(&bar_tfull[as], aphase);
       tc_fence_after();
+      if constexpr (Epi::kProfile) {
+        epi.prof[4] += pc1 - pc0;
+        epi.prof[0] += clock() - pc1;
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(as * kBN + col0);
       epi.tile_body(t, as, taddr);
@@ -297,6 +304,10 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         as = 0;
         aphase ^= 1u;
       }
+    }
+    if constexpr (Epi::kProfile) {
+      if (lane == 0 && ep.dbg)
+        for (int k = 0; k < 6; ++k) atomicAdd(ep.dbg + k, static_cast<unsigned long long>(epi.prof[k]));
     }
   }
 

@@ -20,6 +20,106 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Calibrated compensation of the tensor cores' round-toward-zero accumulation: every
+// tcgen05.mma adds its 16 products to the fp32 accumulator with truncation, which biases a dot
+// product with mostly same-signed terms low by ~(2.8 .. 6.2)e-9 * d (relative; measured on B200
+// with tools/gemm_check `dup` cases for d = 64 .. 4096 and cosines 0.05 .. 1).  The mid value is
+// folded into the row scales (half on each operand) at zero cost in the epilogues; it leaves a
+// residual of <= 2e-9 * d * |a.b| on the distance (3e-6 for unit rows at d = 1536, was 1.9e-5).
+constexpr float kAccumBiasPerDim = 5.2e-9f;
+
+__device__ __forceinline__ float row_inv_scale(int e, int d) {
+  return ldexpf(1.f + 0.5f * kAccumBiasPerDim * static_cast<float>(d), -e);
+}
+
+__device__ __forceinline__ int row_exponent(float ymax) {
+  int e = 0;
+  if (ymax > 0.f && ymax < 3.0e38f) {
+    e = 14 - ilogbf(ymax);
+    e = max(-100, min(100, e));
+  }
+  return e;
+}
+
+__device__ __forceinline__ uint2 pack_half4(__half a, __half b, __half c, __half d) {
+  uint2 r;
+  r.x = static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+  r.y = static_cast<uint32_t>(__half_as_ushort(c)) | (static_cast<uint32_t>(__half_as_ushort(d)) << 16);
+  return r;
+}
+
+// Fast path: d % 4 == 0, 16-byte aligned rows, d <= 128 * kNV.  The row lives in registers
+// (kNV float4 per lane): ONE pass over HBM, float4 loads, 8-byte hi / lo stores.
+template <int kNV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+prep_rows_vec_kernel(const float* __restrict__ x, int rows, int d, long long ldx, int norm_mode,
+                     const int* __restrict__ perm, __half* __restrict__ hi, __half* __restrict__ lo,
+                     int pitch, float* __restrict__ norm, float* __restrict__ inv_scale,
+                     float* __restrict__ xn_out, long long ldxn) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int src = perm ? __ldg(perm + r) : r;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(src) * ldx);
+  const int nvec = d >> 2, pvec = pitch >> 2;
+  float4 v[kNV];
+  float ss = 0.f, amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNV; ++i) {
+    const int k = lane + 32 * i;
+    v[i] = k < nvec ? __ldcs(xr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // same summation order per lane as the generic kernel is NOT required: |x|^2 of the raw row is
+  // only used for the normalisation denominator / un-normalised norms, in fp32 either way
+#pragma unroll
+  for (int i = 0; i < kNV; ++i) {
+    ss = fmaf(v[i].x, v[i].x, ss);
+    ss = fmaf(v[i].y, v[i].y, ss);
+    ss = fmaf(v[i].z, v[i].z, ss);
+    ss = fmaf(v[i].w, v[i].w, ss);
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+  }
+  ss = warp_sum(ss);
+  amax = warp_max(amax);
+  float denom = 1.f;
+  if (norm_mode == PREP_NORM_F_NORMALIZE) denom = fmaxf(sqrtf(ss), 1e-12f);
+  if (norm_mode == PREP_NORM_TRIPLET) denom = sqrtf(ss) + 1e-12f;
+  const bool do_norm = norm_mode != PREP_NORM_NONE;
+  const int e = row_exponent(do_norm ? amax / denom : amax);
+  float ss2 = 0.f;
+  uint2* hr = reinterpret_cast<uint2*>(hi + static_cast<long long>(r) * pitch);
+  uint2* lr = reinterpret_cast<uint2*>(lo + static_cast<long long>(r) * pitch);
+  float4* xo = xn_out ? reinterpret_cast<float4*>(xn_out + static_cast<long long>(src) * ldxn) : nullptr;
+#pragma unroll
+  for (int i = 0; i < kNV; ++i) {
+    const int k = lane + 32 * i;
+    if (k >= pvec) continue;
+    float4 y = v[i];
+    if (do_norm) {
+      y.x = y.x / denom;
+      y.y = y.y / denom;
+      y.z = y.z / denom;
+      y.w = y.w / denom;
+    }
+    if (xo && k < nvec) xo[k] = y;
+    ss2 = fmaf(y.x, y.x, ss2);
+    ss2 = fmaf(y.y, y.y, ss2);
+    ss2 = fmaf(y.z, y.z, ss2);
+    ss2 = fmaf(y.w, y.w, ss2);
+    const float s0 = ldexpf(y.x, e), s1 = ldexpf(y.y, e), s2 = ldexpf(y.z, e), s3 = ldexpf(y.w, e);
+    const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1), h2 = __float2half_rn(s2), h3 = __float2half_rn(s3);
+    hr[k] = pack_half4(h0, h1, h2, h3);
+    lr[k] = pack_half4(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)),
+                       __float2half_rn(s2 - __half2float(h2)), __float2half_rn(s3 - __half2float(h3)));
+  }
+  ss2 = warp_sum(ss2);
+  if (lane == 0) {
+    norm[r] = do_norm ? ss2 : ss;
+    inv_scale[r] = row_inv_scale(e, d);
+  }
+}
+
+// Generic path (any d, any alignment): two passes over the row, scalar accesses.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 prep_rows_kernel(const float* __restrict__ x, int rows, int d, long long ldx, int norm_mode,
                  const int* __restrict__ perm, __half* __restrict__ hi, __half* __restrict__ lo,
@@ -45,13 +145,7 @@ prep_rows_kernel(const float* __restrict__ x, int rows, int d, long long ldx, in
   if (norm_mode == PREP_NORM_F_NORMALIZE) denom = fmaxf(sqrtf(ss), 1e-12f);
   if (norm_mode == PREP_NORM_TRIPLET) denom = sqrtf(ss) + 1e-12f;
   const bool do_norm = norm_mode != PREP_NORM_NONE;
-  const float ymax = do_norm ? amax / denom : amax;  // division is monotone: max|y| exactly
-
-  int e = 0;
-  if (ymax > 0.f && ymax < 3.0e38f) {
-    e = 14 - ilogbf(ymax);
-    e = max(-100, min(100, e));
-  }
+  const int e = row_exponent(do_norm ? amax / denom : amax);  // division is monotone: max|y| exactly
 
   // pass 2: normalise, split, accumulate |y|^2
   float ss2 = 0.f;
@@ -74,7 +168,7 @@ prep_rows_kernel(const float* __restrict__ x, int rows, int d, long long ldx, in
   ss2 = warp_sum(ss2);
   if (lane == 0) {
     norm[r] = do_norm ? ss2 : ss;
-    inv_scale[r] = ldexpf(1.f, -e);
+    inv_scale[r] = row_inv_scale(e, d);
   }
 }
 
@@ -88,9 +182,20 @@ int launch_prep_rows(const float* x, int rows, int d, long long ldx, int norm_mo
   DEMO_REQUIRE(d > 0 && out.pitch >= d && out.pitch % 8 == 0, "prep_rows: bad d/pitch (%d, %d)", d,
                out.pitch);
   const int blocks = ceil_div(rows, kWarpsPerBlock);
-  prep_rows_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-      x, rows, d, ldx, norm_mode, perm, out.hi, out.lo, out.pitch, out.norm, out.inv_scale, xn_out,
-      ldxn);
+  const bool vec = d % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && d <= 2048 &&
+                   (!xn_out || (ldxn % 4 == 0 && (reinterpret_cast<uintptr_t>(xn_out) & 15u) == 0));
+#define DEMO_PREP_VEC(NV)                                                                              \
+  prep_rows_vec_kernel<NV><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(                                \
+      x, rows, d, ldx, norm_mode, perm, out.hi, out.lo, out.pitch, out.norm, out.inv_scale, xn_out, ldxn)
+  if (vec && out.pitch <= 512) DEMO_PREP_VEC(4);
+  else if (vec && out.pitch <= 1024) DEMO_PREP_VEC(8);
+  else if (vec && out.pitch <= 1536) DEMO_PREP_VEC(12);
+  else if (vec && out.pitch <= 2048) DEMO_PREP_VEC(16);
+  else
+    prep_rows_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+        x, rows, d, ldx, norm_mode, perm, out.hi, out.lo, out.pitch, out.norm, out.inv_scale, xn_out,
+        ldxn);
+#undef DEMO_PREP_VEC
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }

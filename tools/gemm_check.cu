@@ -194,6 +194,57 @@ static void self_case(int n, int d, bool normalise) {
   cudaFree(dx); cudaFree(dout); cudaFree(ws);
 }
 
+// Calibration probe for the accumulation bias of the tensor-core path: B row i is a noisy copy of A
+// row i with a prescribed cosine; reports the mean / rms RELATIVE error of the recovered dot
+// product (from d_ii = |a|^2 + |b|^2 - 2ab) against fp64, as a function of d and the cosine.
+static void dup_case(int n, int d, double cosv) {
+  std::vector<float> a, noise, b((size_t)n * d);
+  make_rows(a, n, d, 777, true, 0.0f);
+  make_rows(noise, n, d, 778, true, 0.0f);
+  const double s = std::sqrt(std::max(0.0, 1 - cosv * cosv));
+  for (int i = 0; i < n; ++i) {
+    double ss = 0;
+    for (int k = 0; k < d; ++k) {
+      double v = cosv * a[(size_t)i * d + k] + s * noise[(size_t)i * d + k];
+      b[(size_t)i * d + k] = (float)v;
+      ss += v * v;
+    }
+    float inv = (float)(1 / std::sqrt(ss));
+    for (int k = 0; k < d; ++k) b[(size_t)i * d + k] *= inv;
+  }
+  float *da, *db, *dout;
+  CK(cudaMalloc(&da, a.size() * 4));
+  CK(cudaMalloc(&db, b.size() * 4));
+  CK(cudaMalloc(&dout, (size_t)n * n * 4));
+  CK(cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  size_t wsb = demo_sqdist_workspace_bytes(n, n, d, DEMO_FLAG_SIMT);
+  void* ws;
+  CK(cudaMalloc(&ws, wsb));
+  for (int simt = 0; simt < 2; ++simt) {
+    DK(demo_sqdist_f32(da, db, n, n, d, d, d, dout, n, simt ? DEMO_FLAG_SIMT : 0, nullptr, nullptr, nullptr, ws, wsb, nullptr));
+    CK(cudaDeviceSynchronize());
+    std::vector<float> out((size_t)n * n);
+    CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+    double mean_rel = 0, rms_rel = 0, mean_abs = 0, max_abs = 0, mean_dot = 0;
+    for (int i = 0; i < n; ++i) {
+      double aa = 0, bb = 0, ab = 0;
+      for (int k = 0; k < d; ++k) {
+        double x = a[(size_t)i * d + k], y = b[(size_t)i * d + k];
+        aa += x * x; bb += y * y; ab += x * y;
+      }
+      const double ref = aa + bb - 2 * ab;
+      const double e = (double)out[(size_t)i * n + i] - ref;   // = -2 * (dot_tc - dot)
+      const double rel = -0.5 * e / ab;
+      mean_rel += rel / n; rms_rel += rel * rel / n; mean_abs += e / n; mean_dot += ab / n;
+      max_abs = std::max(max_abs, std::fabs(e));
+    }
+    printf("dup d=%d cos=%.2f %s: dot %.3f  rel dot err mean %+.3e rms %.3e  | dist err mean %+.3e max %.3e | per-d %.3e\n", d, cosv,
+           simt ? "simt" : "tc  ", mean_dot, mean_rel, std::sqrt(rms_rel), mean_abs, max_abs, mean_rel / d);
+  }
+  cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(ws);
+}
+
 int main(int argc, char** argv) {
   if (!demo_device_ok()) {
     printf("no sm_100 device\n");
@@ -216,6 +267,8 @@ int main(int argc, char** argv) {
   self_case(256, 1536, true);
   self_case(256, 4096, true);
   self_case(128, 768, false);
+  for (int d : {64, 256, 768, 1536, 2048, 4096})
+    for (double c : {1.0, 0.9, 0.5, 0.2, 0.05}) dup_case(256, d, c);
   if (argc > 1) {
     bench(1672, 1672, 1536, 20);
     bench(10290, 10290, 1536, 10);
