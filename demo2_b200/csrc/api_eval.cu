@@ -1,7 +1,9 @@
 // extern "C" entry points for the rank-count evaluation (include/demo_b200.h).
 #include <cstdlib>
+#include <cstring>
 
 #include "gemm_epilogues.cuh"
+#include "gemm2_sm100.cuh"
 #include "rank.cuh"
 
 using namespace demo;
@@ -26,7 +28,15 @@ struct EvalWs {
   float* cmc;             // [4096]
   double* map;            // [1]
   int* nvalid;            // [1]
+  TieList ties;           // exact-tie list of the count GEMM (entries + {count, overflow})
 };
+
+// Capacity of the tie list: every valid positive ties with its own threshold (<= T entries per
+// window) plus coincidental bit-equal distances; beyond it the exact tie-fix pass takes over.
+inline unsigned tie_capacity(int Q, long long T) {
+  const long long c = 4 * (T > 0 ? T : 1) + 8ll * (Q > 0 ? Q : 1) + 65536;
+  return static_cast<unsigned>(c < (1ll << 27) ? c : (1ll << 27));
+}
 
 size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w) {
   EvalWs t;
@@ -48,6 +58,9 @@ size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w) {
   t.cmc = c.take<float>(4096);
   t.map = c.take<double>(1);
   t.nvalid = c.take<int>(4);
+  t.ties.cap = tie_capacity(Q, T);
+  t.ties.hdr = c.take<unsigned>(16);
+  t.ties.entries = c.take<int4>(t.ties.cap);
   if (w) *w = t;
   return c.off;
 }
@@ -55,6 +68,25 @@ size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w) {
 __global__ void gidx_kernel(const int* __restrict__ g_perm, int G, int base, int* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < G) out[i] = base + g_perm[i];
+}
+
+// Adds the lexicographic tie corrections recorded by the count GEMM:
+// counts[k] += 1 for every threshold k of the row with t_k == d and g < p_k.
+__global__ void __launch_bounds__(256)
+resolve_ties_kernel(TieList ties, const int* __restrict__ b_gidx, const int* __restrict__ thr_ofs,
+                    const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
+                    const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int window) {
+  if (ties.hdr[1] != 0u) return;  // overflow: the tie-fix GEMM pass handles every tie
+  const unsigned n = min(ties.hdr[0], ties.cap);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 e = ties.entries[i];
+    const int g = __ldg(b_gidx + e.y);
+    const float d = __int_as_float(e.z);
+    const int base = __ldg(thr_ofs + e.x) + window * kWin;
+    const int cnt = max(0, min(kWin, __ldg(thr_cnt + e.x) - window * kWin));
+    for (int k = 0; k < cnt; ++k)
+      if (__ldg(thr_val + base + k) == d && g < __ldg(thr_gidx + base + k)) atomicAdd(counts + base + k, 1u);
+  }
 }
 
 int get_plan(const void* plan, size_t plan_bytes, int Q, int G, PlanView* p) {
@@ -99,46 +131,53 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
   ep.thr_gidx = thr_gidx;
   ep.counts = counts;
   ep.M = Q;
-  ep.dbg = nullptr;
-  if (chunk_tiles <= 0) {
-    // enough units to balance 148 persistent CTAs (>= ~8 units each) but long enough to
+  ep.ties = w.ties;
+  // The fast pass runs on CTA pairs (cta_group::2, 256 x 256 tiles) unless there is a single
+  // 128-row query block or DEMO_COUNT_1CTA is set (A/B timing experiments).
+  static const bool force_1cta = getenv("DEMO_COUNT_1CTA") != nullptr;
+  const bool pair = !force_1cta && Q > kBM;
+  const int n_tiles = ceil_div(G, kBN), m_blocks = ceil_div(Q, pair ? 2 * kBM : kBM);
+  const int workers = pair ? num_sms() / 2 : num_sms();
+  const bool auto_chunk = chunk_tiles <= 0;
+  if (auto_chunk) {
+    // enough units to balance the persistent CTAs (>= ~8 units each) but long enough to
     // amortise the per-unit threshold load / histogram flush
-    const int n_tiles = ceil_div(G, kBN), m_blocks = ceil_div(Q, kBM);
     chunk_tiles = 32;
-    while (chunk_tiles > 1 && static_cast<long long>(m_blocks) * ceil_div(n_tiles, chunk_tiles) < 8ll * num_sms())
+    while (chunk_tiles > 1 && static_cast<long long>(m_blocks) * ceil_div(n_tiles, chunk_tiles) < 8ll * workers)
       chunk_tiles >>= 1;
   }
   const Schedule s = make_chunked_schedule(Q, G, chunk_tiles);
+  GemmOperands ops2;
+  Schedule s2 = s;
+  if (pair) {
+    DEMO_TRY(make_gemm2_operands(w.a, w.b, &ops2));
+    s2 = make_chunked_schedule2(Q, G, chunk_tiles);
+  }
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kWin);
   static const bool no_epi = getenv("DEMO_DEBUG_NOEPI") != nullptr;  // timing experiments only
   for (int wdw = 0; wdw < windows; ++wdw) {
     ep.window = no_epi ? -1 : wdw;
-    static const int dbg = getenv("DEMO_DEBUG_EPI") ? atoi(getenv("DEMO_DEBUG_EPI")) : 0;
-    if (dbg == 1) { DEMO_TRY(launch_sqdist_gemm<EpiCountT<1>>(ops, s, s.num_units, *reinterpret_cast<EpiCountT<1>::Params*>(&ep), stream)); continue; }
-    if (dbg == 2) { DEMO_TRY(launch_sqdist_gemm<EpiCountT<2>>(ops, s, s.num_units, *reinterpret_cast<EpiCountT<2>::Params*>(&ep), stream)); continue; }
-    if (dbg == 3) { DEMO_TRY(launch_sqdist_gemm<EpiCountT<3>>(ops, s, s.num_units, *reinterpret_cast<EpiCountT<3>::Params*>(&ep), stream)); continue; }
-    if (dbg == 4) {
-      static unsigned long long* dptr = nullptr;
-      if (!dptr) cudaMalloc(&dptr, 64);
-      cudaMemsetAsync(dptr, 0, 64, stream);
-      ep.dbg = dptr;
-      cudaEvent_t e0, e1;
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      cudaEventRecord(e0, stream);
-      DEMO_TRY(launch_sqdist_gemm<EpiCountT<4>>(ops, s, s.num_units, *reinterpret_cast<EpiCountT<4>::Params*>(&ep), stream));
-      cudaEventRecord(e1, stream);
-      unsigned long long h[6];
-      cudaMemcpyAsync(h, dptr, 48, cudaMemcpyDeviceToHost, stream);
+    DEMO_CHECK_CUDA(cudaMemsetAsync(w.ties.hdr, 0, 16 * sizeof(unsigned), stream));
+    if (pair) DEMO_TRY(launch_sqdist_gemm2<EpiCount>(ops2, s2, s2.num_units, ep, stream));
+    else DEMO_TRY(launch_sqdist_gemm<EpiCount>(ops, s, s.num_units, ep, stream));
+    resolve_ties_kernel<<<2 * num_sms(), 256, 0, stream>>>(w.ties, w.b_gidx, thr_ofs, thr_cnt, thr_val, thr_gidx,
+                                                            counts, wdw);
+    DEMO_CHECK_CUDA(cudaGetLastError());
+    // exact in-place tie pass; every CTA returns at once unless the list overflowed
+    EpiCountTieFix::Params fix;
+    static_assert(sizeof(fix) == sizeof(ep), "count epilogue parameter blocks must match");
+    memcpy(&fix, &ep, sizeof(fix));
+    DEMO_TRY(launch_sqdist_gemm<EpiCountTieFix>(ops, s, s.num_units, fix, stream));
+    if (getenv("DEMO_DEBUG_TIES")) {
+      unsigned h[16];
+      cudaMemcpyAsync(h, w.ties.hdr, 64, cudaMemcpyDeviceToHost, stream);
       cudaStreamSynchronize(stream);
-      float ms;
-      cudaEventElapsedTime(&ms, e0, e1);
-      const double warps = 8.0 * (s.num_units < num_sms() ? s.num_units : num_sms());
-      printf("[prof] %.2f ms | per epilogue warp, Mcycles: tfull-wait %.1f  tmem-ld %.1f  bisect %.1f  hist %.1f  tile_begin %.1f | chunks/warp %.0f\n",
-             ms, h[0] / warps * 1e-6, h[1] / warps * 1e-6, h[2] / warps * 1e-6, h[3] / warps * 1e-6, h[4] / warps * 1e-6, h[5] / warps);
-      continue;
+      printf("[ties] window %d: %u entries (cap %u), overflow %u, units %d\n", wdw, h[0], w.ties.cap, h[1], s.num_units);
+      if (h[4] + h[8])
+        printf("[prof] tie chunks %u: ld+bisect %.0f  tie-block %.0f  hist %.0f cycles | plain chunks %u: %.0f  %.0f  %.0f\n", h[4],
+               (double)h[5] / h[4], (double)h[6] / h[4], (double)h[7] / h[4], h[8], (double)h[9] / h[8], (double)h[10] / h[8],
+               (double)h[11] / h[8]);
     }
-    DEMO_TRY(launch_sqdist_gemm<EpiCount>(ops, s, s.num_units, ep, stream));
   }
   return DEMO_OK;
 }

@@ -62,7 +62,6 @@ struct EpiColumns {
 // STORE: materialise the matrix (euclidean_distance, cosine_*, re-ranking all-pairs)
 // ---------------------------------------------------------------------------------------
 struct EpiStore {
-  static constexpr bool kProfile = false;
   static constexpr int kStages = 4;
   static constexpr int kSmemBytes = EpiColumns::kBytes;
   struct Params {
@@ -134,16 +133,28 @@ struct EpiStore {
     if (p.rowmax_key && row_ok && vmax > -INFINITY) atomicMax(p.rowmax_key + row, float_key(vmax));
   }
   __device__ void tile_end(const TileInfo&, int) {}
+  __device__ void finish() {}
+  __device__ static bool skip(const Params&) { return false; }
 };
 
 // ---------------------------------------------------------------------------------------
 // COUNT: rank counts without materialising Q x G.
 // A row q keeps up to kWin thresholds (the distances of q's valid positives, ascending by
 // (distance, gallery index)) in a shared-memory column; for every gallery column g the thread
-// finds   b = #{ j : (t_j, p_j) <=lex (d(q,g), g) }   by bisection (top three tree levels in
-// registers) and bumps its private 16-bit histogram bucket b.  At the end of the unit
-// #{g before threshold j} = sum_{b<=j} hist[b]  is added to counts[].  No labels are read:
-// junk / positives are subtracted later from the per-query record list.
+// finds   b = #{ j : t_j <= d(q,g) }   by bisection (top three tree levels in registers) and
+// bumps its private 16-bit histogram bucket b.  At the end of the unit
+//   L_j = #{g : d(q,g) < t_j} = sum_{b<=j} hist[b]   is added to counts[].
+// The lexicographic tie rule ((d, g) before (t_j, p_j) also when d == t_j and g < p_j) is applied
+// OUTSIDE the hot loop: an element whose distance equals a threshold bit for bit (about one per
+// tile: every positive ties with its own threshold, plus coincidences) is appended to a small
+// shared-memory list that is flushed to a global tie list once per unit, and
+// resolve_ties_kernel adds the missing +1s afterwards.  Nothing in the per-element path touches
+// global memory: a global load issued from here queues behind ~7 TB/s of TMA operand traffic and
+// takes microseconds, which used to stall the whole accumulator pipeline (measured: 206 ms ->
+// 150 ms on 20k x 1M).  If the global list overflows (pathological inputs: masses of identical
+// rows) a flag is raised, the resolver stands down and the same GEMM is re-run with
+// EpiCountT<true>, which fixes every tie in place (slow, exact).  No labels are read: junk /
+// positives are subtracted later from the per-query record list.
 // ---------------------------------------------------------------------------------------
 constexpr int kWin = 63;
 
@@ -153,22 +164,29 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
   asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(kOff));  // not volatile: free to schedule
   return v;
 }
-template <int kOff>
 __device__ __forceinline__ void hist_inc_u16(uint32_t addr) {  // ordered read-modify-write
   uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(kOff));
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
   v += 1u;
-  asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(addr), "n"(kOff), "r"(v));
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v));
 }
 
-template <int kDbg>
+// Global tie list header: [0] = entries appended, [1] = overflow flag.
+// Entry = (sorted query row, B row, distance bits, 0).
+struct TieList {
+  int4* entries;
+  unsigned* hdr;
+  unsigned cap;
+};
+
+template <bool kTieFix>
 struct EpiCountT {
-  static constexpr bool kProfile = kDbg == 4;
-  unsigned prof[6] = {0, 0, 0, 0, 0, 0};  // cycles: tfull wait | tmem ld | bisect | hist | tile_begin | chunks
   static constexpr int kStages = 3;
   static constexpr int kRowBytes = 512;  // one bucket row: 128 x f32 thresholds == 256 x u16 counters
-  // columns x2 buffers | thresholds [kWin][128] f32 | histogram [kWin+1][256] u16
-  static constexpr int kSmemBytes = 2 * kBN * 8 + kWin * kRowBytes + (kWin + 1) * kRowBytes;
+  static constexpr int kTieCap = 112;    // per-unit shared tie list, two parities
+  // columns x2 buffers | thresholds [kWin][128] f32 | histogram [kWin+1][256] u16 | tie lists | counters
+  static constexpr int kSmemBytes =
+      2 * kBN * 8 + kWin * kRowBytes + (kWin + 1) * kRowBytes + 2 * kTieCap * 16 + 16;
   struct Params {
     const float* a_norm;
     const float* a_inv;
@@ -182,17 +200,22 @@ struct EpiCountT {
     unsigned* counts;         // += #{gallery columns lexicographically before the threshold}
     int M;
     int window;               // thresholds [window*kWin, window*kWin + kWin) of every row
-    unsigned long long* dbg;  // profiling variant only
+    TieList ties;
   };
+  // The tie-fix pass only runs after an overflow of the tie list.
+  __device__ static bool skip(const Params& p) { return kTieFix && p.ties.hdr[1] == 0u; }
+
   const Params& p;
   float2* s_col;              // [2][kBN]
   float* s_thr;               // [kWin][128]     column = row_in_tile (shared by both column halves)
   unsigned short* s_hist;     // [kWin+1][256]   column = epi_tid (private)
+  int4* s_tie;                // [2][kTieCap]
+  unsigned* s_tie_cnt;        // [2]
   int epi_tid, row_in_tile, col0;
   int hcol;                   // histogram column 2*row + half: the two column halves of a row share a 32-bit
                               // word (low / high u16), so counter b sits at a CONSTANT byte offset
                               // (kWin*512 + 2*half) from threshold b and a warp hits 32 different banks
-  int nthr = 0, tbase = 0;
+  int nthr = 0, tbase = 0, par = 0;
   // top three levels of the search tree live in registers
   float t31 = 0, t15 = 0, t47 = 0, t7 = 0, t23 = 0, t39 = 0, t55 = 0;
 
@@ -201,7 +224,10 @@ struct EpiCountT {
     s_col = reinterpret_cast<float2*>(smem);
     s_thr = reinterpret_cast<float*>(smem + 2 * kBN * 8);
     s_hist = reinterpret_cast<unsigned short*>(smem + 2 * kBN * 8 + kWin * kRowBytes);
+    s_tie = reinterpret_cast<int4*>(smem + 2 * kBN * 8 + kWin * kRowBytes + (kWin + 1) * kRowBytes);
+    s_tie_cnt = reinterpret_cast<unsigned*>(s_tie + 2 * kTieCap);
     hcol = (row_in_tile << 1) | (col0 ? 1 : 0);
+    if (epi_tid < 2) s_tie_cnt[epi_tid] = 0;  // visible after the barrier of the first tile_begin
   }
 
   float2 r_col;
@@ -215,11 +241,26 @@ struct EpiCountT {
   }
   __device__ void stage_store(int as) { s_col[as * kBN + epi_tid] = r_col; }
 
+  __device__ __forceinline__ void push_global(const int4& e) const {
+    const unsigned g = atomicAdd(p.ties.hdr, 1u);
+    if (g < p.ties.cap) p.ties.entries[g] = e;
+    else p.ties.hdr[1] = 1u;
+  }
+  // all epilogue threads; the list of parity `which` is complete (a barrier has been passed)
+  __device__ void flush_ties(int which) const {
+    const int n = min(static_cast<int>(s_tie_cnt[which]), kTieCap);
+    for (int i = epi_tid; i < n; i += kEpiThreads) push_global(s_tie[which * kTieCap + i]);
+  }
+
   __device__ void tile_begin(const TileInfo& t, int as) {
     // everybody has left the previous tile body (s_thr is shared by the two warps of a lane
     // quadrant) and the staged columns of this tile are visible
     epi_bar_sync();
     if (t.first_in_unit) {
+      if (!kTieFix) {
+        flush_ties(par);  // ties of the unit that just ended
+        par ^= 1;
+      }
       const int row = t.m0 + row_in_tile;
       nthr = 0;
       na = ia = 0.f;
@@ -232,8 +273,10 @@ struct EpiCountT {
       // the two threads of a row (column halves) fill alternate threshold slots
       for (int k = (col0 ? 1 : 0); k < kWin; k += 2)
         s_thr[k * 128 + row_in_tile] = k < nthr ? __ldg(p.thr_val + tbase + k) : INFINITY;
-      for (int k = 0; k <= kWin; ++k) s_hist[k * kEpiThreads + hcol] = 0;
+      if (!kTieFix)
+        for (int k = 0; k <= kWin; ++k) s_hist[k * kEpiThreads + hcol] = 0;
       epi_bar_sync();
+      if (!kTieFix && epi_tid == 0) s_tie_cnt[par ^ 1] = 0;  // flushed above; unused until the unit after this one
       const float* thr = s_thr + row_in_tile;
       t31 = thr[31 * 128];
       t15 = thr[15 * 128];
@@ -245,23 +288,12 @@ struct EpiCountT {
     }
   }
 
-  // slow path: full lexicographic bucket #{(t_k, p_k) <=lex (d, g)}
-  __device__ __noinline__ int tie_bucket(float d, int g) const {
-    int pos = 0;
-    for (int k = 0; k < nthr; ++k) {
-      const float tv = s_thr[k * 128 + row_in_tile];
-      if (tv < d || (tv == d && __ldg(p.thr_gidx + tbase + k) <= g)) pos = k + 1;
-    }
-    return pos;
-  }
-
+  // ONE copy of the loop body for both column halves (the histogram offset is a register): the
+  // SM's L1.5 instruction cache holds 32 KB and the unrolled body is ~14 KB; two copies evicted
+  // everything else and every rarely executed path paid an L2 instruction fetch (microseconds
+  // behind the TMA traffic).
   __device__ void tile_body(const TileInfo& t, int as, uint32_t taddr) {
-    if (col0) tile_body_half<1>(t, as, taddr); else tile_body_half<0>(t, as, taddr);  // warp-uniform
-  }
-
-  template <int kHalf>
-  __device__ __forceinline__ void tile_body_half(const TileInfo& t, int as, uint32_t taddr) {
-    constexpr int kHistOff = kWin * kRowBytes + 2 * kHalf;
+    const uint32_t hoff = kWin * kRowBytes + (col0 ? 2 : 0);
     const int row = t.m0 + row_in_tile;
     const bool active = nthr > 0;
     if (p.window < 0) return;  // debug: mainloop-only timing (DEMO_DEBUG_NOEPI)
@@ -275,11 +307,11 @@ struct EpiCountT {
       if (c * kC >= n_here) break;  // warp-uniform
       uint32_t r[kC];
       __syncwarp();
-      unsigned c0 = 0, c1 = 0, c2 = 0;
-      if (kDbg == 4) c0 = clock();
+#ifdef DEMO_PROF
+      const unsigned pc0 = clock();
+#endif
       tmem_ld_32x16(taddr + c * kC, r);
       tmem_ld_wait();
-      if (kDbg == 4) c1 = clock();
       uint32_t slot[kC];   // shared address of the threshold row == bucket, per element
       uint32_t ties = 0;
 #pragma unroll
@@ -299,7 +331,6 @@ struct EpiCountT {
         const bool p3 = u3 <= d;
         a += p3 ? 8 * kRowBytes : 0;
         last = p3 ? u3 : last;
-        if (kDbg == 2 || kDbg == 3) { slot[j] = a + (kDbg == 3 ? (__float_as_uint(d) & 4u) : 0u); continue; }
         // level 4..6 from shared memory (immediate offsets, one predicated add per level)
         float u = lds_f32_off<3 * kRowBytes>(a);
         bool q = u <= d;
@@ -316,45 +347,56 @@ struct EpiCountT {
         ties |= (last == d) ? (1u << j) : 0u;
         slot[j] = a;
       }
+#ifdef DEMO_PROF
+      const bool had_tie = __any_sync(0xffffffffu, ties != 0 && active);
+      const unsigned pc1 = clock();
+#endif
       if (ties && active) {
-        // exact tie with a threshold (rare): thresholds with a larger gallery index sort AFTER this column
+        // the distance equals a threshold bit for bit (rare)
+        do {
+          const int jj = __ffs(ties) - 1;
+          ties &= ties - 1u;
+          uint32_t rj = 0;
 #pragma unroll
-        for (int j = 0; j < kC; ++j) {
-          if (ties >> j & 1u) {
-            const float2 cm = col[c * kC + j];
-            const float d = fmaf(__uint_as_float(r[j]) * ia, cm.x, na + cm.y);
-            slot[j] = thr0 + tie_bucket(d, __ldg(p.b_gidx + t.n0 + col0 + c * kC + j)) * kRowBytes;
+          for (int j = 0; j < kC; ++j) rj = (j == jj) ? r[j] : rj;
+          const float2 cm = col[c * kC + jj];
+          const float d = fmaf(__uint_as_float(rj) * ia, cm.x, na + cm.y);
+          const int bcol = t.n0 + col0 + c * kC + jj;
+          if (!kTieFix) {
+            const int4 e = make_int4(row, bcol, __float_as_int(d), 0);
+            const unsigned i = atomicAdd(s_tie_cnt + par, 1u);
+            if (i < static_cast<unsigned>(kTieCap)) s_tie[par * kTieCap + i] = e;
+            else push_global(e);
+          } else {
+            const int g = __ldg(p.b_gidx + bcol);
+#pragma unroll 1
+            for (int k = 0; k < nthr; ++k)
+              if (s_thr[k * 128 + row_in_tile] == d && g < __ldg(p.thr_gidx + tbase + k))
+                atomicAdd(p.counts + tbase + k, 1u);
           }
-        }
+        } while (ties);
       }
-      if (kDbg == 4) {
-        uint32_t x = 0;
+#ifdef DEMO_PROF
+      __syncwarp();
+      const unsigned pc2 = clock();
+#endif
+      if (!kTieFix) {
 #pragma unroll
-        for (int j = 0; j < kC; ++j) x ^= slot[j];
-        if (x == 0x12345u) prof[5] += 1000;   // forces the slots to be complete here
-        c2 = clock();
+        for (int j = 0; j < kC; ++j) hist_inc_u16(slot[j] + hoff);
       }
-      if (kDbg == 1 || kDbg == 3) {
-        uint32_t x = 0;
-#pragma unroll
-        for (int j = 0; j < kC; ++j) x ^= slot[j];
-        if (x == 0x12345u) hist_inc_u16<kHistOff>(thr0);
-      } else {
-#pragma unroll
-        for (int j = 0; j < kC; ++j) hist_inc_u16<kHistOff>(slot[j]);
-      }
-      if (kDbg == 4) {
-        const unsigned c3 = clock();
-        prof[1] += c1 - c0;
-        prof[2] += c2 - c1;
-        prof[3] += c3 - c2;
-        prof[5] += 1;
-      }
+#ifdef DEMO_PROF
+      const unsigned pc3 = clock();
+      if (had_tie) { prof[0] += 1; prof[1] += pc1 - pc0; prof[2] += pc2 - pc1; prof[3] += pc3 - pc2; }
+      else { prof[4] += 1; prof[5] += pc1 - pc0; prof[6] += pc2 - pc1; prof[7] += pc3 - pc2; }
+#endif
     }
   }
+#ifdef DEMO_PROF
+  unsigned prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
   __device__ void tile_end(const TileInfo& t, int) {
-    if (t.last_in_unit && nthr > 0) {
+    if (!kTieFix && t.last_in_unit && nthr > 0) {
       unsigned run = 0;
       for (int k = 0; k < nthr; ++k) {
         run += s_hist[k * kEpiThreads + hcol];
@@ -362,9 +404,20 @@ struct EpiCountT {
       }
     }
   }
-};
 
-using EpiCount = EpiCountT<0>;
+  // after the last tile of the CTA (all epilogue threads)
+  __device__ void finish() {
+    if (kTieFix) return;
+    epi_bar_sync();
+    flush_ties(par);
+#ifdef DEMO_PROF
+    if ((epi_tid & 31) == 0)
+      for (int k = 0; k < 8; ++k) atomicAdd(p.ties.hdr + 4 + k, prof[k]);
+#endif
+  }
+};
+using EpiCount = EpiCountT<false>;
+using EpiCountTieFix = EpiCountT<true>;
 
 // ---------------------------------------------------------------------------------------
 // EXTRACT: distances of the same-identity pairs (positives + junk) of every query.
@@ -372,7 +425,6 @@ using EpiCount = EpiCountT<0>;
 // [g_lo[q], g_lo[q] + cnt[q]) and the record slot is rec_base[q] + (row - g_lo[q]).
 // ---------------------------------------------------------------------------------------
 struct EpiExtract {
-  static constexpr bool kProfile = false;
   static constexpr int kStages = 4;
   static constexpr int kSmemBytes = EpiColumns::kBytes;
   struct Params {
@@ -427,6 +479,8 @@ struct EpiExtract {
     }
   }
   __device__ void tile_end(const TileInfo&, int) {}
+  __device__ void finish() {}
+  __device__ static bool skip(const Params&) { return false; }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -437,7 +491,6 @@ struct EpiExtract {
 // (ordered distance key << 32 | index code).
 // ---------------------------------------------------------------------------------------
 struct EpiMine {
-  static constexpr bool kProfile = false;
   static constexpr int kStages = 4;
   static constexpr int kSmemBytes = EpiColumns::kBytes;
   struct Params {
@@ -502,6 +555,8 @@ struct EpiMine {
     }
   }
   __device__ void tile_end(const TileInfo&, int) {}
+  __device__ void finish() {}
+  __device__ static bool skip(const Params&) { return false; }
 };
 
 }  // namespace demo

@@ -3,6 +3,7 @@
 #include <cstdarg>
 
 #include "gemm_epilogues.cuh"
+#include "gemm2_sm100.cuh"
 
 namespace demo {
 
@@ -95,6 +96,52 @@ Schedule make_chunked_schedule(int M, int N, int chunk_tiles) {
   s.group_m = 16;
   s.num_units = s.m_blocks * s.n_chunks;
   return s;
+}
+
+int make_gemm2_operands(const PrepView& a, const PrepView& b, GemmOperands* ops) {
+  DEMO_REQUIRE(a.d == b.d, "operand feature dims differ (%d vs %d)", a.d, b.d);
+  DEMO_TRY(make_operand_tensor_map(&ops->a_hi, a.hi, a.rows, a.d, a.pitch, kBM));
+  DEMO_TRY(make_operand_tensor_map(&ops->a_lo, a.lo, a.rows, a.d, a.pitch, kBM));
+  DEMO_TRY(make_operand_tensor_map(&ops->b_hi, b.hi, b.rows, b.d, b.pitch, kBM));  // each CTA loads half a B tile
+  DEMO_TRY(make_operand_tensor_map(&ops->b_lo, b.lo, b.rows, b.d, b.pitch, kBM));
+  ops->num_k_blocks = ceil_div(a.d, kBK);
+  return DEMO_OK;
+}
+
+// Units of the CTA-pair kernel: 256 A rows x chunk_tiles B tiles.
+Schedule make_chunked_schedule2(int M, int N, int chunk_tiles) {
+  Schedule s;
+  s.mode = 1;
+  s.M = M;
+  s.N = N;
+  s.m_block_rows = 2 * kBM;
+  s.m_blocks = ceil_div(M, 2 * kBM);
+  s.n_tiles = ceil_div(N, kBN);
+  s.chunk_tiles = chunk_tiles < 1 ? 1 : chunk_tiles;
+  s.n_chunks = ceil_div(s.n_tiles, s.chunk_tiles);
+  s.group_m = 8;
+  s.num_units = s.m_blocks * s.n_chunks;
+  return s;
+}
+
+int max_active_pairs(const void* kernel, int smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * num_sms());
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return num_sms() / 2;
+  }
+  return n;
 }
 
 Schedule make_list_schedule(int M, int N, const int4* list, const int* list_count) {

@@ -48,6 +48,7 @@ struct Schedule {
   int chunk_tiles = 1;   // mode 1: n-tiles per unit
   int n_chunks = 0;      // mode 1
   int group_m = 16;      // mode 1: m-blocks that share a chunk consecutively
+  int m_block_rows = kBM;  // A rows per unit (2 * kBM for the CTA-pair kernel)
   int num_units = 0;     // modes 0/1
   const int4* list = nullptr;      // mode 2: (m_block, n0, n_rows, _)
   const int* list_count = nullptr; // mode 2: device-side unit count
@@ -73,7 +74,7 @@ __device__ __forceinline__ WorkUnit schedule_get(const Schedule& s, int u) {
     const int g = u / per_group, r = u - g * per_group;
     const int m_in = min(s.group_m, s.m_blocks - g * s.group_m);
     const int c = r / m_in, m = g * s.group_m + (r - c * m_in);
-    w.m0 = m * kBM;
+    w.m0 = m * s.m_block_rows;
     w.n0 = c * s.chunk_tiles * kBN;
     w.n_rows = min(s.chunk_tiles * kBN, s.N - w.n0);
   } else {
@@ -151,6 +152,7 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Schedule sched, const int num_k_blocks, const typename Epi::Params ep) {
   constexpr int kStages = Epi::kStages;
+  if (Epi::skip(ep)) return;  // conditional passes (uniform over the grid, before any setup)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the pointer in the shared address space (plain pointer arithmetic, no integer round trip),
   // otherwise every epilogue access degrades to a generic LD/ST
@@ -280,17 +282,10 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const TileInfo t = cur.info();
       TileCursor nxt = cur;
       nxt.advance();
-      unsigned pc0 = 0, pc1 = 0;
-      if constexpr (Epi::kProfile) pc0 = clock();
       epi.tile_begin(t, as);  // starts with an epilogue-wide barrier: staged columns become visible
       if (nxt.valid()) epi.stage_load(nxt.info());
-      if constexpr (Epi::kProfile) pc1 = clock();
       mbar_wait(&bar_tfull[as], aphase);
       tc_fence_after();
-      if constexpr (Epi::kProfile) {
-        epi.prof[4] += pc1 - pc0;
-        epi.prof[0] += clock() - pc1;
-      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(as * kBN + col0);
       epi.tile_body(t, as, taddr);
@@ -305,10 +300,7 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         aphase ^= 1u;
       }
     }
-    if constexpr (Epi::kProfile) {
-      if (lane == 0 && ep.dbg)
-        for (int k = 0; k < 6; ++k) atomicAdd(ep.dbg + k, static_cast<unsigned long long>(epi.prof[k]));
-    }
+    epi.finish();
   }
 
   tc_fence_before();

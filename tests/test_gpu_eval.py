@@ -155,6 +155,32 @@ def test_fused_eval_duplicates_and_absent_ids(M):
     assert res.num_valid == int((first_o > 0).sum())
 
 
+def test_fused_eval_massive_ties_overflow_path(M):
+    """A gallery made of a few distinct rows repeated hundreds of times: almost every distance ties
+    bit for bit with a threshold, the tie list of the count GEMM overflows and the exact in-place
+    tie pass takes over.  Counts must still equal the oracle's (stable (distance, index) order)."""
+    rng = np.random.default_rng(11)
+    base = rng.standard_normal((6, 256)).astype(np.float32)
+    G, Q = 6000, 260
+    gf = base[rng.integers(0, 6, G)]
+    qf = rng.standard_normal((Q, 256)).astype(np.float32)
+    gp, qp = rng.integers(0, 12, G), rng.integers(0, 12, Q)
+    gc, qc = rng.integers(0, 3, G), rng.integers(0, 3, Q)
+    res = M.evaluate_features(qf, gf, qp, gp, qc, gc, normalize=True)
+    ours = M.sqdist_device(qf, gf, normalize=True).cpu().numpy()
+    ap_o, first_o = _oracle_per_query(ours, qp, gp, qc, gc)
+    np.testing.assert_array_equal(res.first.cpu().numpy(), first_o)
+    np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
+    # moderate ties (below the list capacity): duplicates of a few gallery rows
+    gf2 = rng.standard_normal((G, 256)).astype(np.float32)
+    gf2[1000:1400] = gf2[:400]
+    res = M.evaluate_features(qf, gf2, qp, gp, qc, gc, normalize=True)
+    ours = M.sqdist_device(qf, gf2, normalize=True).cpu().numpy()
+    ap_o, first_o = _oracle_per_query(ours, qp, gp, qc, gc)
+    np.testing.assert_array_equal(res.first.cpu().numpy(), first_o)
+    np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
+
+
 def test_evaluator_drop_in(M):
     from demo2_b200 import synth
     g = load_golden("evaluator_rgbnt201_s0_sigma5")

@@ -28,16 +28,21 @@ del centers
 lab = [torch.from_numpy(x).int().to(dev) for x in (qp, gp, qc, gc)]
 ev = parallel.ShardedEvaluator()
 out = []
+import bench  # noqa: E402
+sampler = bench.ClockSampler(0)
+sampler.start()
 for it in range(iters + 2):
     t = {}
     res = ev.evaluate(qf, gf, lab[0], lab[1], lab[2], lab[3], normalize=True, timers=t)
     torch.cuda.synchronize()
     if it >= 2:
         out.append({k: v[0].elapsed_time(v[1]) for k, v in t.items() if isinstance(v, tuple)})
+clk = sampler.stop()
 keys = out[0].keys()
 print("variant NOEPI=%s EPI=%s  Q=%d G=%d d=%d  mAP %.5f" % (os.environ.get("DEMO_DEBUG_NOEPI"),
                                                             os.environ.get("DEMO_DEBUG_EPI"), Q, G, d, res.mAP))
 print("  " + "  ".join("%s %.2f" % (k, float(np.mean([o[k] for o in out]))) for k in keys))
 cm = float(np.mean([o["count"] for o in out]))
+print("  clocks", clk)
 print("  count: %.2f ms -> %.1f TFLOP/s algorithmic, %.1f executed" % (cm, 2.0 * Q * G * d / cm * 1e-9,
                                                                      6.0 * Q * G * d / cm * 1e-9))
