@@ -173,10 +173,6 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
       cudaMemcpyAsync(h, w.ties.hdr, 64, cudaMemcpyDeviceToHost, stream);
       cudaStreamSynchronize(stream);
       printf("[ties] window %d: %u entries (cap %u), overflow %u, units %d\n", wdw, h[0], w.ties.cap, h[1], s.num_units);
-      if (h[4] + h[8])
-        printf("[prof] tie chunks %u: ld+bisect %.0f  tie-block %.0f  hist %.0f cycles | plain chunks %u: %.0f  %.0f  %.0f\n", h[4],
-               (double)h[5] / h[4], (double)h[6] / h[4], (double)h[7] / h[4], h[8], (double)h[9] / h[8], (double)h[10] / h[8],
-               (double)h[11] / h[8]);
     }
   }
   return DEMO_OK;

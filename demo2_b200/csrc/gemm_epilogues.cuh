@@ -307,9 +307,6 @@ struct EpiCountT {
       if (c * kC >= n_here) break;  // warp-uniform
       uint32_t r[kC];
       __syncwarp();
-#ifdef DEMO_PROF
-      const unsigned pc0 = clock();
-#endif
       tmem_ld_32x16(taddr + c * kC, r);
       tmem_ld_wait();
       uint32_t slot[kC];   // shared address of the threshold row == bucket, per element
@@ -318,39 +315,25 @@ struct EpiCountT {
       for (int j = 0; j < kC; ++j) {
         const float2 cm = col[c * kC + j];
         const float d = fmaf(__uint_as_float(r[j]) * ia, cm.x, na + cm.y);
-        // level 1..3 from registers; `last` tracks the largest threshold <= d (tie detection)
+        // level 1..3 from registers
         const bool p1 = t31 <= d;
         uint32_t a = p1 ? thr0 + 32 * kRowBytes : thr0;
-        float last = p1 ? t31 : -INFINITY;
         const float u2 = p1 ? t47 : t15;
         const bool p2 = u2 <= d;
         a += p2 ? 16 * kRowBytes : 0;
-        last = p2 ? u2 : last;
         const float hi3 = p2 ? t55 : t39, lo3 = p2 ? t23 : t7;
         const float u3 = p1 ? hi3 : lo3;
-        const bool p3 = u3 <= d;
-        a += p3 ? 8 * kRowBytes : 0;
-        last = p3 ? u3 : last;
+        a += (u3 <= d) ? 8 * kRowBytes : 0;
         // level 4..6 from shared memory (immediate offsets, one predicated add per level)
-        float u = lds_f32_off<3 * kRowBytes>(a);
-        bool q = u <= d;
-        a += q ? 4 * kRowBytes : 0;
-        last = q ? u : last;
-        u = lds_f32_off<1 * kRowBytes>(a);
-        q = u <= d;
-        a += q ? 2 * kRowBytes : 0;
-        last = q ? u : last;
-        u = lds_f32_off<0>(a);
-        q = u <= d;
-        a += q ? 1 * kRowBytes : 0;
-        last = q ? u : last;
-        ties |= (last == d) ? (1u << j) : 0u;
+        a += (lds_f32_off<3 * kRowBytes>(a) <= d) ? 4 * kRowBytes : 0;
+        a += (lds_f32_off<1 * kRowBytes>(a) <= d) ? 2 * kRowBytes : 0;
+        a += (lds_f32_off<0>(a) <= d) ? 1 * kRowBytes : 0;
+        // a = thr0 + b * 512 with b = #{t <= d}; the element ties iff t_{b-1} == d.  For b == 0
+        // the probe reads the word below the threshold table (column metadata): a false hit
+        // only costs a tie-list entry, the resolver compares against the real thresholds.
+        ties |= (lds_f32_off<-kRowBytes>(a) == d) ? (1u << j) : 0u;
         slot[j] = a;
       }
-#ifdef DEMO_PROF
-      const bool had_tie = __any_sync(0xffffffffu, ties != 0 && active);
-      const unsigned pc1 = clock();
-#endif
       if (ties && active) {
         // the distance equals a threshold bit for bit (rare)
         do {
@@ -376,24 +359,12 @@ struct EpiCountT {
           }
         } while (ties);
       }
-#ifdef DEMO_PROF
-      __syncwarp();
-      const unsigned pc2 = clock();
-#endif
       if (!kTieFix) {
 #pragma unroll
         for (int j = 0; j < kC; ++j) hist_inc_u16(slot[j] + hoff);
       }
-#ifdef DEMO_PROF
-      const unsigned pc3 = clock();
-      if (had_tie) { prof[0] += 1; prof[1] += pc1 - pc0; prof[2] += pc2 - pc1; prof[3] += pc3 - pc2; }
-      else { prof[4] += 1; prof[5] += pc1 - pc0; prof[6] += pc2 - pc1; prof[7] += pc3 - pc2; }
-#endif
     }
   }
-#ifdef DEMO_PROF
-  unsigned prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
 
   __device__ void tile_end(const TileInfo& t, int) {
     if (!kTieFix && t.last_in_unit && nthr > 0) {
@@ -410,10 +381,6 @@ struct EpiCountT {
     if (kTieFix) return;
     epi_bar_sync();
     flush_ties(par);
-#ifdef DEMO_PROF
-    if ((epi_tid & 31) == 0)
-      for (int k = 0; k < 8; ++k) atomicAdd(p.ties.hdr + 4 + k, prof[k]);
-#endif
   }
 };
 using EpiCount = EpiCountT<false>;
