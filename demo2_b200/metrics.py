@@ -267,9 +267,109 @@ def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=50):
     return r.cmc, r.mAP
 
 
+# Name of the rank-list file eval_func_msrv writes into the working directory, as the reference
+# does unconditionally (utils/metrics.py:38-39, 70-77).  Set to None to skip the file.
+RANK_LIST_FILE = "re.txt"
+
+
+def filtered_rank_lists(distmat, remove_counts, max_rank: int):
+    """Device top-k feeding the rank-list file / ranked-result visualisation: for every query the
+    first ``max_rank + max(remove_counts)`` gallery indices by (distance, index) -- enough to
+    still hold ``max_rank`` items after the caller drops the discarded ones.  Returns an int32
+    host array [Q, k] (np.argsort(distmat, axis=1)[:, :k] at utils/metrics.py:21 / :279)."""
+    from .reranking import topk_rows
+    dist = distmat if isinstance(distmat, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(distmat, np.float32))
+    dist = dist.to(_dev())
+    G = dist.shape[1]
+    k = int(min(G, max_rank + (int(np.max(remove_counts)) if len(remove_counts) else 0)))
+    if k <= 256:
+        return topk_rows(dist, k).cpu().numpy()
+    # more discarded items per query than the top-k kernel holds: full device sort of the rows
+    # (stable, same (distance, index) order); only reached with > 200 same-identity items
+    return torch.sort(dist, dim=1, stable=True).indices[:, :k].to(torch.int32).cpu().numpy()
+
+
+def eval_func_msrv(distmat, q_pids, g_pids, q_camids, g_camids, q_sceneids, g_sceneids, max_rank=50):
+    """utils/metrics.py:12-107 -- MSVR310 protocol: gallery items with the query's pid AND scene
+    id are discarded (:67); cameras only appear in the rank-list file.  CMC / mAP come from the
+    same rank-count kernels as eval_func with the scene ids in the role of the camera ids; the
+    rank-list file (re.txt) is written from a device top-k."""
+    q_pids, g_pids = np.asarray(q_pids), np.asarray(g_pids)
+    q_camids, g_camids = np.asarray(q_camids), np.asarray(g_camids)
+    q_sceneids, g_sceneids = np.asarray(q_sceneids), np.asarray(g_sceneids)
+    dist = distmat if isinstance(distmat, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(distmat, np.float32))
+    dist = dist.to(_dev())
+    num_g = dist.shape[1]
+    r = evaluate_matrix(dist, q_pids, g_pids, q_sceneids, g_sceneids, max_rank)
+    if num_g < max_rank:
+        max_rank = num_g
+    if RANK_LIST_FILE:
+        # discarded items per query = gallery items with the same (pid, scene)
+        key_g = g_pids.astype(np.int64) * (1 << 31) + g_sceneids.astype(np.int64)
+        key_q = q_pids.astype(np.int64) * (1 << 31) + q_sceneids.astype(np.int64)
+        uniq, cnt = np.unique(key_g, return_counts=True)
+        pos = np.searchsorted(uniq, key_q)
+        pos_c = np.minimum(pos, len(uniq) - 1)
+        removed = np.where(uniq[pos_c] == key_q, cnt[pos_c], 0)
+        top = filtered_rank_lists(dist, removed, max_rank)
+        with open(RANK_LIST_FILE, "w") as f:
+            f.write("rank list file\n")
+            for qi in range(len(q_pids)):
+                order = top[qi]
+                keep = ~((g_pids[order] == q_pids[qi]) & (g_sceneids[order] == q_sceneids[qi]))
+                sel = order[keep][:max_rank]
+                f.write("{}_s{}_v{}:\n".format(q_pids[qi], q_sceneids[qi], q_camids[qi]))
+                f.write("".join("{}_s{}_v{}  ".format(a, c, b) for a, b, c in
+                                zip(g_pids[sel], g_camids[sel], g_sceneids[sel])) + "\n")
+    assert r.num_valid > 0, "Error: all query identities do not appear in gallery"  # :101
+    return r.cmc, r.mAP
+
+
 # ------------------------------------------------------------------------------
-# evaluator
+# evaluators
 # ------------------------------------------------------------------------------
+class R1_mAP():
+    """utils/metrics.py:172-218 -- the MSVR310 evaluator.  ``update`` takes the 5-tuple
+    (feat, pid, camid, sceneid, img_path); features are normalised iff ``feat_norm == 'yes'``
+    (:196); ``compute`` returns (cmc, mAP, distmat, pids, camids, qf, gf)."""
+
+    def __init__(self, num_query, max_rank=50, feat_norm='yes'):
+        super(R1_mAP, self).__init__()
+        self.num_query = num_query
+        self.max_rank = max_rank
+        self.feat_norm = feat_norm
+
+    def reset(self):
+        self.feats = []
+        self.pids = []
+        self.camids = []
+        self.sceneids = []
+        self.img_path = []
+
+    def update(self, output):
+        feat, pid, camid, sceneid, img_path = output
+        self.feats.append(feat.detach())
+        self.pids.extend(np.asarray(pid))
+        self.camids.extend(np.asarray(camid.cpu() if isinstance(camid, torch.Tensor) else camid))
+        self.sceneids.extend(np.asarray(sceneid.cpu() if isinstance(sceneid, torch.Tensor) else sceneid))
+        self.img_path.extend(img_path)
+
+    def compute(self):
+        dev = _dev()
+        feats = torch.cat([f.to(dev, non_blocking=True) for f in self.feats], dim=0).float()
+        norm = self.feat_norm == 'yes'
+        if norm:
+            print("The test feature is normalized")
+        nq = self.num_query
+        dist_dev, _, qf, gf = sqdist_device(feats[:nq], feats[nq:], _lib.DIST_SQ, normalize=norm, want_normalized=True)
+        if not norm:
+            qf, gf = feats[:nq], feats[nq:]
+        cmc, mAP = eval_func_msrv(dist_dev, np.asarray(self.pids[:nq]), np.asarray(self.pids[nq:]),
+                                  np.asarray(self.camids[:nq]), np.asarray(self.camids[nq:]),
+                                  np.asarray(self.sceneids[:nq]), np.asarray(self.sceneids[nq:]))
+        return cmc, mAP, dist_dev.cpu().numpy(), self.pids, self.camids, qf, gf
+
+
 class R1_mAP_eval():
     """utils/metrics.py:221-369.  Quirks kept: ``feat_norm`` is truthiness-tested (:343),
     ``compute`` ignores ``self.max_rank`` (:364) and re-ranks with k1=50, k2=15, lambda=0.3 (:359).

@@ -33,30 +33,38 @@ def shard_range(G: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def merge_records(cnt_all: torch.Tensor, recs_all: torch.Tensor):
+def merge_records(cnt_all: torch.Tensor, recs_all: torch.Tensor, sizes=None):
     """cnt_all [P, Q] records per (rank, sorted query); recs_all [P, 3, Tmax] int32 rows
     (dist bits, gidx, junk) in each rank's local CSR order.  Returns the merged CSR offsets
-    [Q+1] (int32) and the merged [3, T_total] records: per query, rank 0's records first."""
+    [Q+1] (int32), the merged [3, T_total] records (per query: rank 0's records first), T_total
+    and the largest per-query count.  Index arithmetic on whole tensors: no per-rank loop and a
+    single device->host read (skipped when the caller passes ``sizes`` = (T_total, max_cnt))."""
     P, Q = cnt_all.shape
+    dev = cnt_all.device
     cnt_all = cnt_all.to(torch.int64)
     total = cnt_all.sum(0)
-    ofs = torch.zeros(Q + 1, dtype=torch.int64, device=cnt_all.device)
+    ofs = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
     ofs[1:] = torch.cumsum(total, 0)
-    T = int(ofs[-1])
+    if sizes is None:
+        host = torch.stack([ofs[-1], total.max() if Q else ofs[-1]]).cpu()
+        T, max_cnt = int(host[0]), int(host[1])
+    else:
+        T, max_cnt = sizes
     merged = torch.zeros((3, max(T, 1)), dtype=torch.int32, device=recs_all.device)
-    rank_prefix = torch.cumsum(cnt_all, 0) - cnt_all
-    qidx_all = torch.arange(Q, device=cnt_all.device)
-    for r in range(P):
-        cnt = cnt_all[r]
-        t_r = int(cnt.sum())
-        if t_r == 0:
-            continue
-        local_ofs = torch.cumsum(cnt, 0) - cnt
-        qidx = torch.repeat_interleave(qidx_all, cnt)
-        within = torch.arange(t_r, device=cnt.device) - local_ofs[qidx]
-        dest = ofs[:-1][qidx] + rank_prefix[r][qidx] + within
-        merged[:, dest] = recs_all[r, :, :t_r]
-    return ofs.to(torch.int32), merged, T, int(total.max()) if Q else 0
+    if T == 0:
+        return ofs.to(torch.int32), merged, T, max_cnt
+    t_max = recs_all.shape[2]
+    cnt_flat = cnt_all.reshape(-1)                                   # (rank, query) pairs, rank-major
+    start_flat = torch.cumsum(cnt_flat, 0) - cnt_flat                # first record of the pair in rank-major order
+    pair = torch.repeat_interleave(torch.arange(P * Q, device=dev), cnt_flat, output_size=T)
+    within = torch.arange(T, device=dev) - start_flat[pair]
+    r, q = pair // Q, pair % Q
+    rank_prefix = (torch.cumsum(cnt_all, 0) - cnt_all).reshape(-1)   # records of lower ranks for the same query
+    rank_start = start_flat.reshape(P, Q)[:, 0]                      # first record of every rank
+    dest = ofs[:-1][q] + rank_prefix[pair] + within
+    src = r * t_max + (torch.arange(T, device=dev) - rank_start[r])
+    merged[:, dest] = recs_all.permute(1, 0, 2).reshape(3, P * t_max)[:, src]
+    return ofs.to(torch.int32), merged, T, max_cnt
 
 
 class CudaEngine:
@@ -157,15 +165,22 @@ class ShardedEvaluator:
         t1 = mark()
         w, recs = eng.records(plan, qf, gf_local, g_index_base, normalize)
         t2 = mark()
+        G_total = plan.G
         if self.world > 1:
+            # one all-gather carries the per-query record counts, the shard's record total and its
+            # gallery size; one host read yields every size the following allocations need
             cnt_local = (plan.rec_ofs[1:] - plan.rec_ofs[:-1]).to(torch.int32)
-            sizes = self._all_gather(torch.tensor([plan.T], dtype=torch.int64, device=cnt_local.device))
-            t_max = int(sizes.max())
-            cnt_all = self._all_gather(cnt_local)
+            meta = torch.tensor([plan.T, plan.G], dtype=torch.int32, device=cnt_local.device)
+            gathered = self._all_gather(torch.cat([cnt_local, meta]))          # [P, Q + 2]
+            cnt_all = gathered[:, :Q]
+            tot = cnt_all.sum(0)
+            host = torch.cat([gathered[:, Q:].reshape(-1).to(torch.int64), tot.max().reshape(1)]).cpu()
+            sizes, gsz = host[:-1].reshape(-1, 2)[:, 0], host[:-1].reshape(-1, 2)[:, 1]
+            t_max, T_sum, G_total, max_all = int(sizes.max()), int(sizes.sum()), int(gsz.sum()), int(host[-1])
             padded = torch.zeros((3, max(t_max, 1)), dtype=torch.int32, device=recs.device)
             padded[:, :plan.T] = recs
             recs_all = self._all_gather(padded)
-            thr_ofs, merged, T, max_cnt = merge_records(cnt_all, recs_all)
+            thr_ofs, merged, T, max_cnt = merge_records(cnt_all, recs_all, sizes=(T_sum, max_all))
         else:
             thr_ofs, merged, T, max_cnt = plan.rec_ofs, recs, plan.T, plan.max_cnt
         t3 = mark()
@@ -178,9 +193,6 @@ class ShardedEvaluator:
         if self.world > 1:
             self._all_reduce_sum(counts)
         t6 = mark()
-        G_total = plan.G
-        if self.world > 1:
-            G_total = int(self._all_gather(torch.tensor([plan.G], dtype=torch.int64, device=counts.device)).sum())
         if G_total < max_rank:
             max_rank = G_total
         cmc_d, scal_d, ap, first = eng.finalize(thr_ofs, thr_cnt, thr_junk, counts, plan.q_perm, Q, max_rank)

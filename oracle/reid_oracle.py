@@ -14,7 +14,9 @@ vectors are committed under ``tests/golden/`` and re-checked by
 ``tests/test_oracle_golden.py``.
 
 Reference lines followed (paths relative to the reference repo):
+  utils/metrics.py:12-107    eval_func_msrv (MSVR310 protocol + re.txt rank-list file)
   utils/metrics.py:110-169   eval_func
+  utils/metrics.py:172-218   R1_mAP (MSVR310 evaluator)
   utils/metrics.py:341-369   R1_mAP_eval.compute (normalise -> split -> dist -> eval)
   utils/metrics.py:395-401   euclidean_distance
   utils/reranking.py:29-100  re_ranking
@@ -99,6 +101,66 @@ def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50, s
     assert len(aps) > 0, "Error: all query identities do not appear in gallery"  # :163
     cmc = np.asarray(cmc_rows).astype(F32).sum(0) / float(len(aps))  # :165-166
     return cmc, np.mean(aps)  # :167
+
+
+def eval_func_msrv(distmat, q_pids, g_pids, q_camids, g_camids, q_sceneids, g_sceneids, max_rank: int = 50,
+                   sort_kind: str = "stable", rank_file=None):
+    """MSVR310 protocol (utils/metrics.py:12-107): a gallery item is discarded for a query when it
+    has the same pid AND the same scene id (:67); cameras only appear in the rank-list file.
+    The reference always (re)writes 're.txt' in the working directory (:38-39, :70-77): one header
+    line, then per query '{pid}_s{scene}_v{cam}:' and the first max_rank kept gallery items as
+    '{pid}_s{scene}_v{cam}  '.  rank_file=None skips the file; the text is returned as third value."""
+    distmat = np.asarray(distmat)
+    q_pids, g_pids = np.asarray(q_pids), np.asarray(g_pids)
+    q_camids, g_camids = np.asarray(q_camids), np.asarray(g_camids)
+    q_sceneids, g_sceneids = np.asarray(q_sceneids), np.asarray(g_sceneids)
+    num_q, num_g = distmat.shape
+    if num_g < max_rank:  # :18-20
+        max_rank = num_g
+        print("Note: number of gallery samples is quite small, got {}".format(num_g))
+    order_all = np.argsort(distmat, axis=1, kind=sort_kind)  # :21
+    lines = ["rank list file\n"]  # :38-39
+    cmc_rows, aps = [], []
+    for qi in range(num_q):
+        order = order_all[qi]
+        same_pid = g_pids[order] == q_pids[qi]
+        remove = same_pid & (g_sceneids[order] == q_sceneids[qi])  # :67
+        keep = ~remove
+        lines.append("{}_s{}_v{}:\n".format(q_pids[qi], q_sceneids[qi], q_camids[qi]))  # :71
+        lines.append("".join("{}_s{}_v{}  ".format(a, c, b) for a, b, c in
+                             zip(g_pids[order][keep][:max_rank], g_camids[order][keep][:max_rank],
+                                 g_sceneids[order][keep][:max_rank])) + "\n")  # :72-77
+        hits = same_pid[keep].astype(np.int32)  # :81
+        if not hits.any():  # :82-84
+            continue
+        cum = hits.cumsum()
+        first = cum.copy()
+        first[first > 1] = 1
+        cmc_rows.append(first[:max_rank])
+        prec = cum / (np.arange(1, cum.shape[0] + 1) * 1.0)
+        aps.append((prec * hits).sum() / hits.sum())
+    assert len(aps) > 0, "Error: all query identities do not appear in gallery"  # :101
+    text = "".join(lines)
+    if rank_file:
+        with open(rank_file, "w") as f:
+            f.write(text)
+    cmc = np.asarray(cmc_rows).astype(F32).sum(0) / float(len(aps))
+    return cmc, np.mean(aps), text
+
+
+def r1_map_msrv(feats, pids, camids, sceneids, num_query: int, feat_norm="yes", rank_file=None):
+    """R1_mAP.compute (utils/metrics.py:193-218): normalise iff feat_norm == 'yes', split, squared
+    distance, eval_func_msrv."""
+    feats = np.asarray(feats, F32)
+    if feat_norm == "yes":
+        feats = l2_normalize(feats)
+    qf, gf = feats[:num_query], feats[num_query:]
+    pids, camids, sceneids = np.asarray(pids), np.asarray(camids), np.asarray(sceneids)
+    distmat = euclidean_distance(qf, gf)
+    cmc, mAP, text = eval_func_msrv(distmat, pids[:num_query], pids[num_query:], camids[:num_query],
+                                    camids[num_query:], sceneids[:num_query], sceneids[num_query:],
+                                    rank_file=rank_file)
+    return cmc, mAP, distmat, qf, gf, text
 
 
 def rank_counts(distmat, q_pids, g_pids, q_camids, g_camids):

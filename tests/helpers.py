@@ -27,6 +27,13 @@ def make_case(shape: str, seed: int, sigma: float, gallery_is_query: bool = Fals
     return qf, gf, s.q_pids, s.g_pids, s.q_camids, s.g_camids
 
 
+def make_scene_ids(num_q: int, num_g: int, seed: int, nscene: int = 6):
+    """Scene ids for the MSVR310 protocol (utils/metrics.py:67), seeded separately so the other
+    cases stay unchanged."""
+    rng = np.random.default_rng(100000 + seed)
+    return rng.integers(0, nscene, num_q), rng.integers(0, nscene, num_g)
+
+
 def sample_index(n_rows: int, n_cols: int, count: int = 4096):
     """Deterministic scattered sample of a matrix (flat indices)."""
     total = n_rows * n_cols

@@ -232,3 +232,48 @@ def test_eval_edge_cases():
                                         np.array([0]), np.array([1, 1, 1, 1]))
     np.testing.assert_array_equal(idx, [1, 3])
     np.testing.assert_array_equal(r, [2, 4])
+
+
+# ---------------------------------------------------------------------------------------------
+# MSVR310 protocol (eval_func_msrv / R1_mAP, utils/metrics.py:12-107, 172-218)
+# ---------------------------------------------------------------------------------------------
+def test_msrv_oracle_matches_reference_on_its_matrix(tmp_path):
+    """Same matrix in -> same CMC / mAP and the same rank-list file, byte for byte."""
+    import hashlib
+    from tests.helpers import make_scene_ids
+    g = load_golden("msrv_msvr310_s1_small")
+    _, _, qp, gp, qc, gc = make_case("msvr310", 1, 4.0)
+    qp, gp, qc, gc = qp[:60], gp[:300], qc[:60], gc[:300]
+    qs, gs = make_scene_ids(60, 300, 1)
+    f = tmp_path / "re.txt"
+    cmc, mAP, text = oracle.eval_func_msrv(g["dist"], qp, gp, qc, gc, qs, gs, rank_file=str(f))
+    np.testing.assert_allclose(cmc, g["cmc"], atol=1e-7)
+    assert abs(mAP - float(g["mAP"])) < 1e-12
+    assert text.encode() == g["text"].tobytes()
+    assert f.read_text() == text
+    assert hashlib.sha256(text.encode()).digest() == g["text_sha256"].tobytes()
+    # scene ids in the role of camera ids give the same metrics through eval_func
+    cmc2, mAP2 = oracle.eval_func(g["dist"], qp, gp, qs, gs)
+    np.testing.assert_array_equal(cmc, cmc2)
+    assert mAP == mAP2
+
+
+def test_msrv_oracle_full_shape_and_evaluator():
+    from tests.helpers import make_scene_ids
+    from demo2_b200 import synth
+    g = load_golden("msrv_msvr310_s0")
+    qf, gf, qp, gp, qc, gc = make_case("msvr310", 0, 4.0)
+    qs, gs = make_scene_ids(len(qp), len(gp), 0)
+    cmc, mAP, text = oracle.eval_func_msrv(oracle.euclidean_distance(qf, gf), qp, gp, qc, gc, qs, gs)
+    assert abs(mAP - float(g["mAP"])) < 5e-6           # across two fp32 GEMMs
+    np.testing.assert_allclose(cmc, g["cmc"], atol=2.5 / len(qp))
+    assert len(text) == int(g["text_len"])
+    s = synth.make_named("msvr310", sigma=4.0, seed=2)
+    qs, gs = make_scene_ids(len(s.q_pids), len(s.g_pids), 2)
+    g2 = load_golden("msrv_evaluator_msvr310_s2")
+    cmc, mAP, dist, *_ = oracle.r1_map_msrv(np.concatenate([s.qf.numpy(), s.gf.numpy()]),
+                                            np.concatenate([s.q_pids, s.g_pids]),
+                                            np.concatenate([s.q_camids, s.g_camids]), np.concatenate([qs, gs]),
+                                            s.num_query)
+    assert abs(mAP - float(g2["mAP"])) < 5e-6
+    np.testing.assert_allclose(dist.ravel()[sample_index(*dist.shape)], g2["dist_sample"], rtol=1e-5, atol=2e-6)
