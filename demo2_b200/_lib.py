@@ -48,6 +48,13 @@ SIGNATURES = {
     "demo_rerank": (i32, [vp, i32, i32, i32, i64, i32, i32, i32, C.c_double, vp, i64, i32, vp, i64, vp, vp, sz, vp]),
     "demo_rerank_matrix": (i32, [vp, i64, i32, i32, i32, i32, C.c_double, vp, i64, vp, sz, vp]),
     "demo_topk_rows": (i32, [vp, i32, i32, i64, i32, vp, vp, vp]),
+    "demo_rerank_dims": (i32, [i32, i32, i32, c_i32p, c_i32p, c_i32p]),
+    "demo_rerank_shard_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
+    "demo_rerank_shard_topk": (i32, [vp, i32, i32, i32, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]),
+    "demo_rerank_shard_krecip": (i32, [i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
+    "demo_rerank_shard_expand": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "demo_rerank_shard_jaccard": (i32, [i32, i32, i32, i32, i32, C.c_double, i32, i32, i32, vp, vp, vp, vp, i64, vp,
+                                        sz, vp]),
     "demo_triplet_workspace_bytes": (sz, [i32, i32]),
     "demo_triplet_hard_fwd": (i32, [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "demo_triplet_hard_bwd": (i32, [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp]),

@@ -146,12 +146,12 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
     while (chunk_tiles > 1 && static_cast<long long>(m_blocks) * ceil_div(n_tiles, chunk_tiles) < 8ll * workers)
       chunk_tiles >>= 1;
   }
-  const Schedule s = make_chunked_schedule(Q, G, chunk_tiles);
+  const Schedule s = make_chunked_schedule(Q, G, chunk_tiles, w.a.pitch);
   GemmOperands ops2;
   Schedule s2 = s;
   if (pair) {
     DEMO_TRY(make_gemm2_operands(w.a, w.b, &ops2));
-    s2 = make_chunked_schedule2(Q, G, chunk_tiles);
+    s2 = make_chunked_schedule2(Q, G, chunk_tiles, w.a.pitch);
   }
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kWin);
   static const bool no_epi = getenv("DEMO_DEBUG_NOEPI") != nullptr;  // timing experiments only

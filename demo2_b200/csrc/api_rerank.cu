@@ -31,9 +31,133 @@ size_t carve_rr(Carver& c, int N, int Q, int d, int k1, int k2, RrWs* w) {
   return c.off;
 }
 
+// Row-sharded re-ranking: workspace of one rank owning up to rows_cap rows.
+struct RrShardWs {
+  PrepView a;           // all N rows prepared (features are replicated)
+  float* E;             // [rows_cap][N]  local rows of the all-pairs matrix
+  unsigned* rowmax_key; // [rows_cap]
+  float* rowmax;        // [rows_cap]
+  RerankWs r;           // inverted index / scan scratch (the full-size sparse arrays are the caller's)
+};
+
+size_t carve_rr_shard(Carver& c, int N, int Q, int d, int k1, int k2, int rows_cap, RrShardWs* w) {
+  RrShardWs t;
+  const size_t n = N > 0 ? N : 1, rc = rows_cap > 0 ? rows_cap : 1;
+  prep_carve(c, N, d > 0 ? d : 8, &t.a);
+  t.E = c.take<float>(rc * n);
+  t.rowmax_key = c.take<unsigned>(rc);
+  t.rowmax = c.take<float>(rc);
+  rerank_carve(c, N, Q, k1, k2, &t.r);
+  if (w) *w = t;
+  return c.off;
+}
+
+int get_rr_shard(void* ws, size_t ws_bytes, int N, int Q, int d, int k1, int k2, int rows_cap, RrShardWs* w) {
+  Carver c(ws, ws_bytes);
+  carve_rr_shard(c, N, Q, d, k1, k2, rows_cap, w);
+  if (!ws || !c.ok()) {
+    set_error("rerank shard: workspace missing or too small (%zu < %zu)", ws_bytes, c.off);
+    return DEMO_ERR_WORKSPACE;
+  }
+  return DEMO_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+// ---- row-sharded re-ranking (multi-GPU; the host all-gathers between the stages) ----
+int demo_rerank_dims(int N, int k1, int k2, int* K, int* cap, int* capq) {
+  if (K) *K = rerank_k(k1, k2);
+  if (cap) *cap = rerank_cap(k1);
+  if (capq) *capq = rerank_capq(N, k1, k2);
+  return DEMO_OK;
+}
+
+size_t demo_rerank_shard_workspace_bytes(int N, int Q, int d, int k1, int k2, int rows_cap) {
+  Carver c(nullptr, ~size_t(0));
+  return round_up(carve_rr_shard(c, N, Q, d, k1, k2, rows_cap, nullptr), size_t(1024));
+}
+
+// Stage 1: rows [row0, row0+nrows) of the all-pairs squared-distance matrix (kept in the
+// workspace with their row maxima) and their K = max(k1+1, k2) nearest neighbours by
+// (E[i][j] / rowmax_i, j)  ->  rank_rows [nrows][K]   (utils/reranking.py:38-48).
+int demo_rerank_shard_topk(const float* feat, int N, int Q, int d, int64_t ld, int flags, int k1, int k2, int row0,
+                           int nrows, int rows_cap, int* rank_rows, float* feat_n_out, void* ws, size_t ws_bytes,
+                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEMO_REQUIRE(feat && N > 1 && Q >= 1 && Q < N && d > 0 && ld >= d, "rerank shard: bad arguments (N=%d, Q=%d)", N, Q);
+  DEMO_REQUIRE(row0 >= 0 && nrows >= 0 && nrows <= rows_cap && row0 + nrows <= N, "rerank shard: bad row range");
+  RrShardWs w;
+  DEMO_TRY(get_rr_shard(ws, ws_bytes, N, Q, d, k1, k2, rows_cap, &w));
+  const int nm = (flags & DEMO_FLAG_L2NORM) ? PREP_NORM_F_NORMALIZE : PREP_NORM_NONE;
+  DEMO_TRY(launch_prep_rows(feat, N, d, ld, nm, nullptr, w.a, feat_n_out, d, stream));
+  if (nrows == 0) return DEMO_OK;
+  DEMO_REQUIRE(rank_rows, "rerank shard: null output");
+  PrepView rows = w.a;  // the local rows as the A operand
+  rows.hi += static_cast<size_t>(row0) * w.a.pitch;
+  rows.lo += static_cast<size_t>(row0) * w.a.pitch;
+  rows.norm += row0;
+  rows.inv_scale += row0;
+  rows.rows = nrows;
+  GemmOperands ops;
+  DEMO_TRY(make_gemm_operands(rows, w.a, &ops));
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.rowmax_key, 0, sizeof(unsigned) * nrows, stream));
+  EpiStore::Params ep;
+  ep.a_norm = rows.norm;
+  ep.a_inv = rows.inv_scale;
+  ep.b_norm = w.a.norm;
+  ep.b_inv = w.a.inv_scale;
+  ep.out = w.E;
+  ep.ldo = N;
+  ep.M = nrows;
+  ep.mode = DIST_SQ;
+  ep.rowmax_key = w.rowmax_key;
+  const Schedule s = make_dense_schedule(nrows, N);
+  DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+  keys_to_float_kernel2<<<ceil_div(nrows, 256), 256, 0, stream>>>(w.rowmax_key, w.rowmax, nrows);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  return launch_topk_rows(w.E, N, nrows, N, w.rowmax, rerank_k(k1, k2), rank_rows, nullptr, stream);
+}
+
+// Stage 2: V rows of the local rows from the gathered neighbour lists (:51-71); writes rows
+// [row0, row0+nrows) of the full-size arrays v_idx [.][cap], v_val (fp16), v_cnt.
+int demo_rerank_shard_krecip(int N, int Q, int d, int k1, int k2, int row0, int nrows, int rows_cap,
+                             const int* rank_all, int* v_idx, void* v_val, int* v_cnt, void* ws, size_t ws_bytes,
+                             void* stream_) {
+  RrShardWs w;
+  DEMO_TRY(get_rr_shard(ws, ws_bytes, N, Q, d, k1, k2, rows_cap, &w));
+  DEMO_REQUIRE(rank_all && v_idx && v_val && v_cnt, "rerank shard: null pointer");
+  return launch_krecip_rows(w.E, N, w.rowmax, rank_all, N, k1, k2, row0, nrows, v_idx, static_cast<__half*>(v_val),
+                            v_cnt, static_cast<cudaStream_t>(stream_));
+}
+
+// Stage 3: local query expansion of the local rows from the gathered V rows (:73-78).
+int demo_rerank_shard_expand(int N, int k1, int k2, int row0, int nrows, const int* rank_all, const int* v_idx,
+                             const void* v_val, const int* v_cnt, int* q_idx, void* q_val, int* q_cnt,
+                             void* stream_) {
+  DEMO_REQUIRE(rank_all && v_idx && v_val && v_cnt && q_idx && q_val && q_cnt, "rerank shard: null pointer");
+  return launch_expand_rows(rank_all, N, k1, k2, row0, nrows, v_idx, static_cast<const __half*>(v_val), v_cnt, q_idx,
+                            static_cast<__half*>(q_val), q_cnt, static_cast<cudaStream_t>(stream_));
+}
+
+// Stage 4: inverted index of the gathered final V (f_* = q_* arrays, or v_* when k2 == 1), then
+// Jaccard + blend for the local query rows -> out_rows [nq_local][N-Q], nq_local =
+// max(0, min(row0+nrows, Q) - row0)   (:80-99).
+int demo_rerank_shard_jaccard(int N, int Q, int d, int k1, int k2, double lambda_value, int row0, int nrows,
+                              int rows_cap, const int* f_idx, const void* f_val, const int* f_cnt, float* out_rows,
+                              int64_t ldo, void* ws, size_t ws_bytes, void* stream_) {
+  RrShardWs w;
+  DEMO_TRY(get_rr_shard(ws, ws_bytes, N, Q, d, k1, k2, rows_cap, &w));
+  DEMO_REQUIRE(f_idx && f_val && f_cnt, "rerank shard: null pointer");
+  int nq_local = (row0 + nrows < Q ? row0 + nrows : Q) - row0;
+  if (nq_local < 0) nq_local = 0;
+  DEMO_REQUIRE(nq_local == 0 || (out_rows && ldo >= N - Q), "rerank shard: bad output");
+  const int f_cap = k2 != 1 ? rerank_capq(N, k1, k2) : rerank_cap(k1);
+  return launch_jaccard_rows(w.E, N, w.rowmax, N, Q, lambda_value, row0, nq_local, f_idx,
+                             static_cast<const __half*>(f_val), f_cnt, f_cap, w.r, out_rows, ldo,
+                             static_cast<cudaStream_t>(stream_));
+}
 
 size_t demo_rerank_workspace_bytes(int N, int Q, int d, int k1, int k2) {
   Carver c(nullptr, ~size_t(0));

@@ -1,6 +1,7 @@
 // Host side of the tcgen05 distance GEMM: TMA tensor maps, schedules, and the SIMT (FFMA)
 // reference kernel used as an on-device self-check of the tensor-core path.
 #include <cstdarg>
+#include <cstdlib>
 
 #include "gemm_epilogues.cuh"
 #include "gemm2_sm100.cuh"
@@ -84,7 +85,21 @@ Schedule make_dense_schedule(int M, int N) {
   return s;
 }
 
-Schedule make_chunked_schedule(int M, int N, int chunk_tiles) {
+// How many row blocks of A share a gallery chunk back to back.  The persistent CTAs take
+// consecutive units, so at any moment they work on `group_m` different A blocks times a few B
+// chunks: B is swept from HBM once per group (each tile is then served to the group from L2),
+// so the groups should be as large as the A blocks of one group fit comfortably in L2 (each is
+// re-streamed for every tile).  ncu on 20k x 1M with groups of 8 pairs: 386 GB of DRAM reads per
+// launch for 6.3 GB of operands.
+static int balanced_group_m(int m_blocks, int block_rows, int d_pitch) {
+  const double block_bytes = static_cast<double>(block_rows) * d_pitch * 4.0;   // hi + lo
+  int cap = static_cast<int>(32e6 / (block_bytes > 1 ? block_bytes : 1));  // measured best on 20k x 1M: 20 pairs
+  if (cap < 4) cap = 4;
+  const int n_groups = ceil_div(m_blocks, cap);
+  return ceil_div(m_blocks, n_groups > 0 ? n_groups : 1);
+}
+
+Schedule make_chunked_schedule(int M, int N, int chunk_tiles, int d_pitch) {
   Schedule s;
   s.mode = 1;
   s.M = M;
@@ -93,7 +108,7 @@ Schedule make_chunked_schedule(int M, int N, int chunk_tiles) {
   s.n_tiles = ceil_div(N, kBN);
   s.chunk_tiles = chunk_tiles < 1 ? 1 : chunk_tiles;
   s.n_chunks = ceil_div(s.n_tiles, s.chunk_tiles);
-  s.group_m = 16;
+  s.group_m = balanced_group_m(s.m_blocks, kBM, d_pitch);
   s.num_units = s.m_blocks * s.n_chunks;
   return s;
 }
@@ -109,7 +124,7 @@ int make_gemm2_operands(const PrepView& a, const PrepView& b, GemmOperands* ops)
 }
 
 // Units of the CTA-pair kernel: 256 A rows x chunk_tiles B tiles.
-Schedule make_chunked_schedule2(int M, int N, int chunk_tiles) {
+Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch) {
   Schedule s;
   s.mode = 1;
   s.M = M;
@@ -119,7 +134,8 @@ Schedule make_chunked_schedule2(int M, int N, int chunk_tiles) {
   s.n_tiles = ceil_div(N, kBN);
   s.chunk_tiles = chunk_tiles < 1 ? 1 : chunk_tiles;
   s.n_chunks = ceil_div(s.n_tiles, s.chunk_tiles);
-  s.group_m = 8;
+  s.group_m = balanced_group_m(s.m_blocks, 2 * kBM, d_pitch);
+  if (const char* e = getenv("DEMO_GROUP_M")) s.group_m = atoi(e) > 0 ? atoi(e) : s.group_m;  // experiments
   s.num_units = s.m_blocks * s.n_chunks;
   return s;
 }

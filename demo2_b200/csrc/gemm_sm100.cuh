@@ -322,7 +322,7 @@ struct GemmOperands {
 int make_gemm_operands(const PrepView& a, const PrepView& b, GemmOperands* ops);
 
 Schedule make_dense_schedule(int M, int N);
-Schedule make_chunked_schedule(int M, int N, int chunk_tiles);
+Schedule make_chunked_schedule(int M, int N, int chunk_tiles, int d_pitch);
 Schedule make_list_schedule(int M, int N, const int4* list, const int* list_count);
 
 template <class Epi>

@@ -325,7 +325,7 @@ constexpr int kMaxK = 128;  // k1 + 1 <= kMaxK
 __global__ void __launch_bounds__(kKrThreads)
 krecip_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ rowmax,
               const int* __restrict__ rank, int K, int N, int k1, int kh, int cap, int* __restrict__ v_idx,
-              __half* __restrict__ v_val, int* __restrict__ v_cnt) {
+              __half* __restrict__ v_val, int* __restrict__ v_cnt, int row0) {
   extern __shared__ unsigned s_dyn[];
   const int words = ceil_div(N, 32);
   unsigned* bm_kri = s_dyn;            // reciprocal set R(i, k1)
@@ -337,7 +337,9 @@ krecip_kernel(const float* __restrict__ E, long long lde, const float* __restric
   __shared__ int s_nkri;
   __shared__ unsigned s_scan[kKrThreads + 1];
   __shared__ float s_sum;
-  const int i = blockIdx.x, t = threadIdx.x;
+  // block li works on global row i = row0 + li; E / rowmax hold only the caller's rows (local
+  // index), the neighbour lists and the V rows are indexed globally (row-sharded re-ranking)
+  const int li = blockIdx.x, i = li + row0, t = threadIdx.x;
   const int K1 = k1 + 1;
   for (int w = t; w < 2 * words; w += kKrThreads) s_dyn[w] = 0;
   if (t < K1) s_fwd[t] = rank[(long long)i * K + t];
@@ -389,8 +391,8 @@ krecip_kernel(const float* __restrict__ E, long long lde, const float* __restric
   __syncthreads();
   const int n = bm_enumerate(bm_exp, words, s_list, cap, s_scan);  // np.unique: sorted ascending
   const int nn = min(n, cap);
-  const float div = rowmax[i];
-  const float* erow = E + (long long)i * lde;
+  const float div = rowmax[li];
+  const float* erow = E + (long long)li * lde;
   for (int p = t; p < nn; p += kKrThreads) s_w[p] = expf(-(erow[s_list[p]] / div));
   __syncthreads();
   if (t == 0) s_sum = np_pairwise_sum(s_w, nn);
@@ -411,14 +413,14 @@ constexpr int kQeThreads = 128;
 __global__ void __launch_bounds__(kQeThreads)
 expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const int* __restrict__ v_idx,
               const __half* __restrict__ v_val, const int* __restrict__ v_cnt, int capq,
-              int* __restrict__ q_idx, __half* __restrict__ q_val, int* __restrict__ q_cnt) {
+              int* __restrict__ q_idx, __half* __restrict__ q_val, int* __restrict__ q_cnt, int row0) {
   extern __shared__ unsigned s_dyn[];
   const int words = ceil_div(N, 32);
   unsigned* bm = s_dyn;
   int* s_list = reinterpret_cast<int*>(s_dyn + words);  // [capq]
   __shared__ unsigned s_scan[kQeThreads + 1];
   __shared__ int s_nb[64];
-  const int i = blockIdx.x, t = threadIdx.x;
+  const int i = blockIdx.x + row0, t = threadIdx.x;
   for (int w = t; w < words; w += kQeThreads) bm[w] = 0;
   if (t < k2) s_nb[t] = rank[(long long)i * K + t];
   __syncthreads();
@@ -487,10 +489,10 @@ jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restri
                const int* __restrict__ idx, const __half* __restrict__ val, const int* __restrict__ cnt, int cap,
                const int* __restrict__ inv_ofs, const int* __restrict__ inv_row, const __half* __restrict__ inv_val,
                float one_minus_lambda_h, float lambda_f, __half* __restrict__ scratch, float* __restrict__ out,
-               long long ldo) {
+               long long ldo, int row0) {
   extern __shared__ __half s_tmin[];
-  const int i = blockIdx.x, t = threadIdx.x;
-  __half* tmin = scratch ? scratch + (long long)i * N : s_tmin;
+  const int li = blockIdx.x, i = li + row0, t = threadIdx.x;   // E / rowmax / scratch / out: local rows
+  __half* tmin = scratch ? scratch + (long long)li * N : s_tmin;
   for (int j = t; j < N; j += kJcThreads) tmin[j] = __float2half_rn(0.f);
   __syncthreads();
   const int c = cnt[i];
@@ -508,13 +510,13 @@ jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restri
   }
   const __half one = __float2half_rn(1.f), two = __float2half_rn(2.f);
   const __half w = __float2half_rn(one_minus_lambda_h);
-  const float div = rowmax[i];
+  const float div = rowmax[li];
   const int G = N - Q;
   for (int g = t; g < G; g += kJcThreads) {
     const __half tm = tmin[Q + g];
     const __half jac = np_hsub(one, np_hdiv(tm, np_hsub(two, tm)));           // 1 - tmin / (2 - tmin)
-    const float od = E[(long long)i * lde + Q + g] / div;
-    out[(long long)i * ldo + g] = __fadd_rn(__half2float(np_hmul(jac, w)), __fmul_rn(od, lambda_f));  // (:95), no FMA contraction
+    const float od = E[(long long)li * lde + Q + g] / div;
+    out[(long long)li * ldo + g] = __fadd_rn(__half2float(np_hmul(jac, w)), __fmul_rn(od, lambda_f));  // (:95), no FMA contraction
   }
 }
 
@@ -616,7 +618,7 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
     const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(w.cap) * 8;
     DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d too large for the shared-memory bitmaps", N);
     DEMO_CHECK_CUDA(cudaFuncSetAttribute(krecip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    krecip_kernel<<<N, kKrThreads, smem, stream>>>(E, lde, rowmax, w.rank, K, N, k1, kh, w.cap, w.v_idx, w.v_val, w.v_cnt);
+    krecip_kernel<<<N, kKrThreads, smem, stream>>>(E, lde, rowmax, w.rank, K, N, k1, kh, w.cap, w.v_idx, w.v_val, w.v_cnt, 0);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
   const int* f_idx = w.v_idx;
@@ -628,7 +630,7 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
     DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d / k2=%d too large for the expansion kernel", N, k2);
     DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     expand_kernel<<<N, kQeThreads, smem, stream>>>(w.rank, K, N, k2, w.cap, w.v_idx, w.v_val, w.v_cnt, w.capq, w.q_idx,
-                                                   w.q_val, w.q_cnt);
+                                                   w.q_val, w.q_cnt, 0);
     DEMO_CHECK_CUDA(cudaGetLastError());
     f_idx = w.q_idx;
     f_val = w.q_val;
@@ -649,9 +651,67 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
     DEMO_CHECK_CUDA(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     jaccard_kernel<<<Q, kJcThreads, smem, stream>>>(E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w.inv_ofs, w.inv_row,
                                                     w.inv_val, oml, static_cast<float>(lambda_value), w.tmin_scratch, out,
-                                                    ldo);
+                                                    ldo, 0);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
+  return DEMO_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Row-sharded stages (multi-GPU re-ranking): a rank owns the contiguous rows
+// [row0, row0 + nrows) of the N x N problem.  E / rowmax are LOCAL ([nrows][lde] / [nrows]);
+// the neighbour lists and the sparse V rows are full-size arrays that the host all-gathers
+// between the stages, so every kernel indexes them by global row.
+// ---------------------------------------------------------------------------------------
+int launch_krecip_rows(const float* E, long long lde, const float* rowmax, const int* rank_all, int N, int k1,
+                       int k2, int row0, int nrows, int* v_idx, __half* v_val, int* v_cnt, cudaStream_t stream) {
+  DEMO_REQUIRE(k1 >= 1 && k1 + 1 <= kMaxK && k1 + 1 <= N, "re_ranking: need 1 <= k1 < min(N, %d) (k1=%d, N=%d)", kMaxK, k1, N);
+  if (nrows <= 0) return DEMO_OK;
+  const int K = rerank_k(k1, k2), kh = rerank_kh(k1), cap = rerank_cap(k1), words = ceil_div(N, 32);
+  const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(cap) * 8;
+  DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d too large for the shared-memory bitmaps", N);
+  DEMO_CHECK_CUDA(cudaFuncSetAttribute(krecip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  krecip_kernel<<<nrows, kKrThreads, smem, stream>>>(E, lde, rowmax, rank_all, K, N, k1, kh, cap, v_idx, v_val, v_cnt, row0);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  return DEMO_OK;
+}
+
+int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int nrows, const int* v_idx,
+                       const __half* v_val, const int* v_cnt, int* q_idx, __half* q_val, int* q_cnt,
+                       cudaStream_t stream) {
+  DEMO_REQUIRE(k2 >= 2 && k2 <= 64 && k2 <= N, "re_ranking: expansion needs 2 <= k2 <= min(N, 64) (k2=%d)", k2);
+  if (nrows <= 0) return DEMO_OK;
+  const int K = rerank_k(k1, k2), cap = rerank_cap(k1), capq = rerank_capq(N, k1, k2), words = ceil_div(N, 32);
+  const size_t smem = static_cast<size_t>(words) * 4 + static_cast<size_t>(capq) * 4;
+  DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d / k2=%d too large for the expansion kernel", N, k2);
+  DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  expand_kernel<<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx, q_val,
+                                                     q_cnt, row0);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  return DEMO_OK;
+}
+
+// Inverted index over ALL N rows of the (gathered) final V, then the Jaccard / blend rows of the
+// local queries [row0, row0 + nq_local), row0 + nq_local <= Q.
+int launch_jaccard_rows(const float* E, long long lde, const float* rowmax, int N, int Q, double lambda_value,
+                        int row0, int nq_local, const int* f_idx, const __half* f_val, const int* f_cnt, int f_cap,
+                        const RerankWs& w, float* out, long long ldo, cudaStream_t stream) {
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int) * (N + 1), stream));
+  inv_count_kernel<<<N, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, N, w.col_cnt);
+  size_t tmp = w.cub_bytes;
+  DEMO_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.col_cnt, w.inv_ofs, N + 1, stream));
+  inv_fill_kernel<<<N, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, N, w.inv_ofs, w.cursor, w.inv_row, w.inv_val);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  if (nq_local <= 0) return DEMO_OK;
+  const float oml = __half2float(__double2half(1.0 - lambda_value));
+  const size_t smem = w.tmin_scratch ? 0 : static_cast<size_t>(N) * 2;
+  DEMO_CHECK_CUDA(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  jaccard_kernel<<<nq_local, kJcThreads, smem, stream>>>(E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w.inv_ofs,
+                                                         w.inv_row, w.inv_val, oml, static_cast<float>(lambda_value),
+                                                         w.tmin_scratch, out, ldo, row0);
+  DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }
 

@@ -243,3 +243,138 @@ def evaluate_gallery_chunks(qf, gf, q_pid, g_pid, q_cam, g_cam, n_chunks: int, n
     scal = scal_d.cpu()
     return EvalResult(cmc_d.cpu().numpy(), np.float64(scal[0].item()), int(scal[1:2].view(torch.int32)[0].item()),
                       ap, first)
+
+
+# ------------------------------------------------------------------------------------------------
+# Row-sharded k-reciprocal re-ranking (second row)
+# ------------------------------------------------------------------------------------------------
+class CudaRerankEngine:
+    """The four re-ranking stages of one rank on its GPU (C ABI demo_rerank_shard_*)."""
+
+    def __init__(self):
+        self.lib = _lib.require_device()
+
+    def dims(self, N, k1, k2):
+        K, cap, capq = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.demo_rerank_dims(N, k1, k2, C.byref(K), C.byref(cap), C.byref(capq)))
+        return K.value, cap.value, capq.value
+
+    def begin(self, feat, Q, k1, k2, row0, nrows, rows_cap, normalize):
+        from .metrics import _features, _ws
+        self.feat = _features(feat)
+        self.N, self.d = self.feat.shape
+        self.Q, self.k1, self.k2 = Q, k1, k2
+        self.row0, self.nrows, self.rows_cap = row0, nrows, rows_cap
+        self.flags = _lib.FLAG_L2NORM if normalize else 0
+        self.nbytes = self.lib.demo_rerank_shard_workspace_bytes(self.N, Q, self.d, k1, k2, rows_cap)
+        self.ws = _ws(self.nbytes)
+        return self.feat.device
+
+    def topk(self, rank_rows):
+        check(self.lib.demo_rerank_shard_topk(ptr(self.feat), self.N, self.Q, self.d, self.feat.stride(0), self.flags,
+                                              self.k1, self.k2, self.row0, self.nrows, self.rows_cap, ptr(rank_rows),
+                                              None, ptr(self.ws), self.nbytes, stream_ptr()))
+
+    def krecip(self, rank_all, v_idx, v_val, v_cnt):
+        check(self.lib.demo_rerank_shard_krecip(self.N, self.Q, self.d, self.k1, self.k2, self.row0, self.nrows,
+                                                self.rows_cap, ptr(rank_all), ptr(v_idx), ptr(v_val), ptr(v_cnt),
+                                                ptr(self.ws), self.nbytes, stream_ptr()))
+
+    def expand(self, rank_all, v_idx, v_val, v_cnt, q_idx, q_val, q_cnt):
+        check(self.lib.demo_rerank_shard_expand(self.N, self.k1, self.k2, self.row0, self.nrows, ptr(rank_all),
+                                                ptr(v_idx), ptr(v_val), ptr(v_cnt), ptr(q_idx), ptr(q_val),
+                                                ptr(q_cnt), stream_ptr()))
+
+    def jaccard(self, f_idx, f_val, f_cnt, lambda_value, out_rows):
+        check(self.lib.demo_rerank_shard_jaccard(self.N, self.Q, self.d, self.k1, self.k2, float(lambda_value),
+                                                 self.row0, self.nrows, self.rows_cap, ptr(f_idx), ptr(f_val),
+                                                 ptr(f_cnt), ptr(out_rows), out_rows.stride(0) if out_rows.numel() else
+                                                 self.N - self.Q, ptr(self.ws), self.nbytes, stream_ptr()))
+
+
+class ShardedReranker:
+    """re_ranking(probFea, galFea, k1, k2, lambda) with the rows of the N x N problem split
+    contiguously over the ranks (features replicated):
+
+        every rank   distances of its rows against all N rows + their nearest neighbours   [tcgen05 GEMM, top-k]
+        all ranks    all-gather the neighbour lists                  (N x K int32)
+        every rank   k-reciprocal sets + softmax weights of its rows -> sparse V rows
+        all ranks    all-gather the sparse V rows                    (N x cap: int32 index, fp16 weight)
+        every rank   local query expansion of its rows
+        all ranks    all-gather the expanded rows                    (N x capq)
+        every rank   inverted index (whole V, redundantly) + Jaccard / blend of its query rows
+        all ranks    all-gather the [Q, G] result rows
+
+    Every stage is row-local given the gathered lists, so the result is bit-identical to the
+    single-GPU re_ranking.  ``ranks`` > 1 with world == 1 runs the ranks one after another on one
+    device (the same data flow without a process group; used by the single-GPU tests)."""
+
+    def __init__(self, world: int = 1, rank: int = 0, group=None, engine_factory=None):
+        self.world, self.rank, self.group = world, rank, group
+        self.engine_factory = engine_factory if engine_factory is not None else CudaRerankEngine
+
+    def _all_gather_rows(self, full: torch.Tensor, rpr: int):
+        """In-place all-gather of equal row slices: rank r owns rows [r*rpr, (r+1)*rpr)."""
+        import torch.distributed as dist
+        mine = full[self.rank * rpr:(self.rank + 1) * rpr]
+        dist.all_gather_into_tensor(full, mine.clone(), group=self.group)
+
+    def re_ranking(self, probFea, galFea, k1: int, k2: int, lambda_value: float, normalize: bool = False,
+                   emulate_ranks: int | None = None):
+        P = emulate_ranks if emulate_ranks else self.world
+        ranks = range(P) if emulate_ranks else [self.rank]
+        engines = {r: self.engine_factory() for r in ranks}
+        q = probFea if isinstance(probFea, torch.Tensor) else torch.as_tensor(np.asarray(probFea))
+        g = galFea if isinstance(galFea, torch.Tensor) else torch.as_tensor(np.asarray(galFea))
+        Q, G = q.shape[0], g.shape[0]
+        N = Q + G
+        feat = torch.cat([q.float(), g.float().to(q.device)], dim=0)
+        rpr = -(-N // P)                       # rows per rank (the last ranks may own fewer / none)
+        n_pad = rpr * P
+        dev = None
+        for r in ranks:
+            row0 = min(r * rpr, N)
+            dev = engines[r].begin(feat, Q, int(k1), int(k2), row0, min(rpr, N - row0), rpr, normalize)
+        K, cap, capq = engines[ranks[0]].dims(N, int(k1), int(k2))
+        rank_all = torch.zeros((n_pad, K), dtype=torch.int32, device=dev)
+        v_idx = torch.zeros((n_pad, cap), dtype=torch.int32, device=dev)
+        v_val = torch.zeros((n_pad, cap), dtype=torch.float16, device=dev)
+        v_cnt = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+        gather = (lambda t: self._all_gather_rows(t, rpr)) if (self.world > 1 and not emulate_ranks) else (lambda t: None)
+
+        for r in ranks:
+            engines[r].topk(rank_all[min(r * rpr, N):])
+        gather(rank_all)
+        for r in ranks:
+            engines[r].krecip(rank_all, v_idx, v_val, v_cnt)
+        for t in (v_idx, v_val, v_cnt):
+            gather(t)
+        f_idx, f_val, f_cnt = v_idx, v_val, v_cnt
+        if int(k2) != 1:
+            q_idx = torch.zeros((n_pad, capq), dtype=torch.int32, device=dev)
+            q_val = torch.zeros((n_pad, capq), dtype=torch.float16, device=dev)
+            q_cnt = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+            for r in ranks:
+                engines[r].expand(rank_all, v_idx, v_val, v_cnt, q_idx, q_val, q_cnt)
+            for t in (q_idx, q_val, q_cnt):
+                gather(t)
+            f_idx, f_val, f_cnt = q_idx, q_val, q_cnt
+        # result rows: rank r owns the queries [r*rpr, (r+1)*rpr) & [0, Q)
+        qs = min(rpr, Q)                       # largest number of query rows one rank can own
+        out = torch.empty((Q, G), dtype=torch.float32, device=dev)
+        local = {}
+        for r in ranks:
+            local[r] = torch.zeros((qs, G), dtype=torch.float32, device=dev)
+            engines[r].jaccard(f_idx, f_val, f_cnt, lambda_value, local[r])
+        if self.world > 1 and not emulate_ranks:
+            import torch.distributed as dist
+            buf = torch.empty((P * qs, G), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(buf, local[self.rank], group=self.group)
+            pieces = {r: buf[r * qs:(r + 1) * qs] for r in range(P)}
+        else:
+            pieces = local
+        for r in range(P):
+            lo, hi = min(r * rpr, Q), min((r + 1) * rpr, Q)
+            if hi > lo:
+                out[lo:hi] = pieces[r][:hi - lo]
+        return out

@@ -135,6 +135,28 @@ DEMO_API int demo_rerank_matrix(const float* X, int64_t ldx, int N, int Q, int k
 DEMO_API int demo_topk_rows(const float* mat, int rows, int cols, int64_t ld, int k, int* idx_out,
                             float* val_out, void* stream);
 
+/* Row-sharded re-ranking (multi-GPU): rank r owns the contiguous rows
+ * [row0, row0+nrows) of the N x N problem, features are replicated, and the HOST all-gathers the
+ * neighbour lists (after _topk), the sparse V rows (after _krecip) and the expanded rows (after
+ * _expand) -- full-size caller-owned arrays rank_all [N][K] int32, v_idx [N][cap] int32,
+ * v_val [N][cap] fp16, v_cnt [N], q_idx / q_val [N][capq], q_cnt [N]; K / cap / capq from
+ * demo_rerank_dims.  Every stage is bit-identical to the corresponding part of demo_rerank. */
+DEMO_API int demo_rerank_dims(int N, int k1, int k2, int* K, int* cap, int* capq);
+DEMO_API size_t demo_rerank_shard_workspace_bytes(int N, int Q, int d, int k1, int k2, int rows_cap);
+DEMO_API int demo_rerank_shard_topk(const float* feat, int N, int Q, int d, int64_t ld, int flags, int k1, int k2,
+                                    int row0, int nrows, int rows_cap, int* rank_rows, float* feat_n_out,
+                                    void* ws, size_t ws_bytes, void* stream);
+DEMO_API int demo_rerank_shard_krecip(int N, int Q, int d, int k1, int k2, int row0, int nrows, int rows_cap,
+                                      const int* rank_all, int* v_idx, void* v_val, int* v_cnt, void* ws,
+                                      size_t ws_bytes, void* stream);
+DEMO_API int demo_rerank_shard_expand(int N, int k1, int k2, int row0, int nrows, const int* rank_all,
+                                      const int* v_idx, const void* v_val, const int* v_cnt, int* q_idx,
+                                      void* q_val, int* q_cnt, void* stream);
+DEMO_API int demo_rerank_shard_jaccard(int N, int Q, int d, int k1, int k2, double lambda_value, int row0,
+                                       int nrows, int rows_cap, const int* f_idx, const void* f_val,
+                                       const int* f_cnt, float* out_rows, int64_t ldo, void* ws, size_t ws_bytes,
+                                       void* stream);
+
 /* ---- batch-hard triplet mining -------------------------------------------------------------
  * demo_triplet_hard_fwd replaces the core of TripletLoss.__call__ (layers/triplet_loss.py:124-125):
  * euclidean_dist(x, x) + hard_example_mining(dist_mat, labels, return_inds=True) fused into the

@@ -244,13 +244,15 @@ def _np_sum_f32(w):
     return np.sum(w)  # numpy pairwise float32 sum
 
 
-def k_reciprocal_rows(od, rank, k1: int):
+def k_reciprocal_rows(od, rank, k1: int, row0: int = 0):
     """utils/reranking.py:51-71.  Returns per-row (sorted unique index array,
-    float16 weights) -- the non-zeros of V before query expansion."""
+    float16 weights) -- the non-zeros of V before query expansion.  ``od`` may hold only the
+    rows [row0, row0 + len(od)) of the normalised matrix (row-sharded tests); ``rank`` is global."""
     n = od.shape[0]
     kh = int(np.around(k1 / 2)) + 1  # half-to-even (appendix A7)
     rows = []
-    for i in range(n):
+    for li in range(n):
+        i = li + row0
         fwd = rank[i, : k1 + 1]
         bwd = rank[fwd, : k1 + 1]
         kri = fwd[np.nonzero(bwd == i)[0]]
@@ -262,7 +264,7 @@ def k_reciprocal_rows(od, rank, k1: int):
             if len(np.intersect1d(ckri, kri)) > 2 / 3 * len(ckri):
                 expn = np.append(expn, ckri)
         expn = np.unique(expn)
-        w = np.exp(-od[i, expn])  # float32
+        w = np.exp(-od[li, expn])  # float32
         rows.append((expn.astype(np.int64), (w / _np_sum_f32(w)).astype(F16)))
     return rows
 

@@ -120,3 +120,16 @@ def test_evaluator_with_reranking(M):
     assert distmat.shape == (836, 836)
     assert abs(mAP - float(g["rr_mAP"])) < 2e-4
     np.testing.assert_allclose(cmc, g["rr_cmc"], atol=2.5 / 836)
+
+
+@pytest.mark.parametrize("shape,k1,k2,ranks", [("rgbnt201", 20, 6, 2), ("rgbnt201", 20, 1, 3), ("msvr310", 50, 15, 4)])
+def test_row_sharded_reranking_is_bit_identical(shape, k1, k2, ranks):
+    """The multi-GPU data flow (parallel.ShardedReranker: per-rank row ranges through the
+    demo_rerank_shard_* stages, gathered neighbour lists / sparse V rows) with the ranks executed one
+    after another on one device == single-GPU re_ranking, bit for bit."""
+    from demo2_b200 import parallel, reranking
+    qf, gf, *_ = make_case(shape, 0, 5.0)
+    whole = reranking.re_ranking_device(qf, gf, k1, k2, 0.3)
+    sharded = parallel.ShardedReranker().re_ranking(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda(), k1, k2,
+                                                    0.3, emulate_ranks=ranks)
+    assert torch.equal(whole, sharded)

@@ -178,3 +178,101 @@ def test_merge_records_layout():
     ofs, merged, T, max_cnt = parallel.merge_records(cnt, recs)
     assert ofs.tolist() == [0, 3, 6, 7] and T == 7 and max_cnt == 3
     assert merged[1].tolist() == [10, 11, 20, 21, 22, 23, 12]
+
+
+# ---------------------------------------------------------------------------------------------
+# row-sharded re-ranking (parallel.ShardedReranker): gloo, numpy stage engine
+# ---------------------------------------------------------------------------------------------
+class NumpyRerankEngine:
+    """Stage interface of parallel.CudaRerankEngine on the host, from the oracle's pieces.
+    (Every rank forms the full all-pairs matrix -- cheap at test size -- and keeps its rows of
+    E = D^T, so that E[i][j] / rowmax_i is exactly the oracle's od[i][j].)"""
+    F16, F32 = np.float16, np.float32
+
+    def dims(self, N, k1, k2):
+        kh = int(np.around(k1 / 2)) + 1
+        cap = (k1 + 1) * (kh + 1)
+        return max(k1 + 1, k2), cap, min(N, max(k2, 1) * cap)
+
+    def begin(self, feat, Q, k1, k2, row0, nrows, rows_cap, normalize):
+        f = np.asarray(feat, np.float32)
+        if normalize:
+            f = oracle.l2_normalize(f)
+        D = oracle.euclidean_distance(f, f)
+        self.N, self.Q, self.k1, self.k2, self.row0, self.nrows = len(f), Q, k1, k2, row0, nrows
+        E = np.ascontiguousarray(D[:, row0:row0 + nrows].T)
+        self.od = (E / E.max(axis=1, keepdims=True)).astype(np.float32) if nrows else E
+        return torch.device("cpu")
+
+    def topk(self, rank_rows):
+        if self.nrows:
+            rank_rows.numpy()[:self.nrows] = oracle.stable_topk(self.od, max(self.k1 + 1, self.k2))
+
+    def krecip(self, rank_all, v_idx, v_val, v_cnt):
+        rows = oracle.k_reciprocal_rows(self.od, rank_all.numpy(), self.k1, row0=self.row0)
+        for li, (idx, val) in enumerate(rows):
+            i = self.row0 + li
+            keep = val != 0
+            n = int(keep.sum())
+            v_idx.numpy()[i, :n], v_val.numpy()[i, :n], v_cnt.numpy()[i] = idx[keep], val[keep], n
+
+    def expand(self, rank_all, v_idx, v_val, v_cnt, q_idx, q_val, q_cnt):
+        vi, vv, vc, rk = v_idx.numpy(), v_val.numpy(), v_cnt.numpy(), rank_all.numpy()
+        for i in range(self.row0, self.row0 + self.nrows):
+            acc = {}
+            for nb in rk[i, :self.k2]:
+                for c, v in zip(vi[nb, :vc[nb]].tolist(), vv[nb, :vc[nb]].astype(np.float32).tolist()):
+                    acc[c] = np.float32(acc.get(c, np.float32(0.0)) + np.float32(v))
+            cols = np.fromiter(sorted(acc), dtype=np.int64, count=len(acc))
+            vals = (np.array([acc[c] for c in cols.tolist()], np.float32) / np.float32(self.k2)).astype(np.float16)
+            keep = vals != 0
+            n = int(keep.sum())
+            q_idx.numpy()[i, :n], q_val.numpy()[i, :n], q_cnt.numpy()[i] = cols[keep], vals[keep], n
+
+    def jaccard(self, f_idx, f_val, f_cnt, lambda_value, out_rows):
+        fi, fv, fc = f_idx.numpy(), f_val.numpy(), f_cnt.numpy()
+        n, Q = self.N, self.Q
+        inv_rows = [[] for _ in range(n)]
+        inv_vals = [[] for _ in range(n)]
+        for t in range(n):
+            for c, v in zip(fi[t, :fc[t]].tolist(), fv[t, :fc[t]].tolist()):
+                inv_rows[c].append(t)
+                inv_vals[c].append(v)
+        inv_rows = [np.asarray(a, np.int64) for a in inv_rows]
+        inv_vals = [np.asarray(a, np.float16) for a in inv_vals]
+        for i in range(self.row0, min(self.row0 + self.nrows, Q)):
+            temp_min = np.zeros(n, dtype=np.float16)
+            for j, vij in zip(fi[i, :fc[i]].tolist(), fv[i, :fc[i]]):
+                t = inv_rows[j]
+                temp_min[t] = temp_min[t] + np.minimum(vij, inv_vals[j])
+            jac = 1 - temp_min / (2 - temp_min)
+            final = jac * (1 - lambda_value) + self.od[i - self.row0] * lambda_value
+            out_rows.numpy()[i - self.row0] = final[Q:].astype(np.float32)
+
+
+def _rr_worker(rank, world, port, qf, gf, k1, k2, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rr = parallel.ShardedReranker(world=world, rank=rank, group=dist.group.WORLD, engine_factory=NumpyRerankEngine)
+        out[rank] = rr.re_ranking(torch.from_numpy(qf), torch.from_numpy(gf), k1, k2, 0.3).numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,k1,k2", [(2, 8, 3), (3, 6, 1)])
+def test_sharded_reranking_matches_oracle(world, k1, k2):
+    qf, gf, *_ = make_case("rgbnt201", 1, 5.0)
+    qf, gf = qf[:37, :96].copy(), gf[:90, :96].copy()      # N = 127: ragged row shards
+    ref = oracle.re_ranking(qf, gf, k1, k2, 0.3)
+    # the same flow without a process group (ranks emulated one after another)
+    emu = parallel.ShardedReranker(engine_factory=NumpyRerankEngine).re_ranking(
+        torch.from_numpy(qf), torch.from_numpy(gf), k1, k2, 0.3, emulate_ranks=world).numpy()
+    np.testing.assert_array_equal(emu, ref)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rr_worker, args=(world, _free_port(), qf, gf, k1, k2, out), nprocs=world, join=True)
+    assert len(out) == world
+    for r in range(world):
+        np.testing.assert_array_equal(out[r], ref)
