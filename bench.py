@@ -44,6 +44,17 @@ def workload_desc(name):
                                                            {"large": 3, "rgbnt100": 2, "rgbnt201": 0}[name]))
 
 
+def load_traffic(name, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/),
+    valid for the workload / GPU count it was captured on; None otherwise."""
+    p = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        if j.get("workload") == name and j.get("n_gpus") == world:
+            return j
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -327,6 +338,7 @@ def run_ours(args):
     h2d = (q_host.numel() + g_host.numel()) * 4 + sum(v.numel() * 4 for v in lab_host.values())
     d2h = 4096 * 4 + 8 + 16 + 32  # metrics slab (cmc | mAP | num_valid) + plan info
 
+    traffic = load_traffic(name, world)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -344,9 +356,13 @@ def run_ours(args):
                                "features + labels to the device and reads cmc/mAP back; the upload of step i+1 is "
                                "issued on a copy stream while step i computes (serial_* = no overlap)"},
                 "gpu_launches": launches * args.steps,
-                "roofline": {"bound": "tensor", "kernel": "sqdist_gemm_kernel<EpiCount> (fused distance + rank-count)",
+                "roofline": {"bound": "tensor",
+                             "kernel": "sqdist_gemm2_kernel<EpiCount> (CTA-pair tcgen05 GEMM, fused distance + rank-count)",
                              "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": None, "ms_per_launch": count_ms,
+                             "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                             "traffic_note": (traffic["note"] if traffic else
+                                              "no ncu capture for this workload / GPU count (see profiles/)"),
+                             "ms_per_launch": count_ms,
                              "peak_note": "%s bf16 sustained %.1f TFLOP/s / %d fp16 split passes (hi*hi + hi*lo + lo*hi); "
                                           "achieved = 2*Q*G_local*d algorithmic flop / CUDA-event time"
                                           % (peaks["source"], peaks["bf16_tflops_sustained"], passes),

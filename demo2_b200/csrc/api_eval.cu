@@ -138,11 +138,12 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
   const bool pair = !force_1cta && Q > kBM;
   const int n_tiles = ceil_div(G, kBN), m_blocks = ceil_div(Q, pair ? 2 * kBM : kBM);
   const int workers = pair ? num_sms() / 2 : num_sms();
+  if (const char* e = getenv("DEMO_CHUNK_TILES")) chunk_tiles = atoi(e);  // experiments
   const bool auto_chunk = chunk_tiles <= 0;
   if (auto_chunk) {
     // enough units to balance the persistent CTAs (>= ~8 units each) but long enough to
     // amortise the per-unit threshold load / histogram flush
-    chunk_tiles = 32;
+    chunk_tiles = 8;   // L2 super-tile: see balanced_group_m (gemm_host.cu)
     while (chunk_tiles > 1 && static_cast<long long>(m_blocks) * ceil_div(n_tiles, chunk_tiles) < 8ll * workers)
       chunk_tiles >>= 1;
   }

@@ -20,6 +20,8 @@
 //   tempty[a]  leader only; 2 x 8 epilogue warps arrive (the peer's warps remotely)
 #pragma once
 
+#include <cstdlib>
+
 #include "gemm_sm100.cuh"
 
 namespace demo {
@@ -284,6 +286,7 @@ int launch_sqdist_gemm2(const GemmOperands& ops, const Schedule& sched, int max_
       set_error("CTA-pair kernel cannot be scheduled on this device");
       return DEMO_ERR_CUDA;
     }
+    if (const char* e = getenv("DEMO_PAIRS")) pairs = atoi(e) > 0 && atoi(e) < pairs ? atoi(e) : pairs;  // experiments
   }
   const int grid = 2 * (max_units < pairs ? max_units : pairs);
   kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo, sched,

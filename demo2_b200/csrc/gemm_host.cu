@@ -85,18 +85,18 @@ Schedule make_dense_schedule(int M, int N) {
   return s;
 }
 
-// How many row blocks of A share a gallery chunk back to back.  The persistent CTAs take
-// consecutive units, so at any moment they work on `group_m` different A blocks times a few B
-// chunks: B is swept from HBM once per group (each tile is then served to the group from L2),
-// so the groups should be as large as the A blocks of one group fit comfortably in L2 (each is
-// re-streamed for every tile).  ncu on 20k x 1M with groups of 8 pairs: 386 GB of DRAM reads per
-// launch for 6.3 GB of operands.
-static int balanced_group_m(int m_blocks, int block_rows, int d_pitch) {
+// How many row blocks of A share a gallery chunk back to back.  The persistent workers (CTAs or
+// CTA pairs) take consecutive units, so in one "round" they cover group_m A blocks x
+// (workers / group_m) B chunks -- an L2-level super-tile.  group_m divides the worker count so
+// that the rounds stay aligned with the chunks, and is the largest such divisor whose A blocks
+// (re-streamed for every tile) stay below ~64 MB.  Measured on 20k x 1M (74 pairs): groups of
+// 37 pairs x 8-tile chunks 162 ms / 298 GB of DRAM reads, groups of 8 x 32 tiles 167 ms / 386 GB.
+static int balanced_group_m(int m_blocks, int block_rows, int d_pitch, int workers) {
   const double block_bytes = static_cast<double>(block_rows) * d_pitch * 4.0;   // hi + lo
-  int cap = static_cast<int>(32e6 / (block_bytes > 1 ? block_bytes : 1));  // measured best on 20k x 1M: 20 pairs
-  if (cap < 4) cap = 4;
-  const int n_groups = ceil_div(m_blocks, cap);
-  return ceil_div(m_blocks, n_groups > 0 ? n_groups : 1);
+  int best = 1;
+  for (int g = 1; g <= workers; ++g)
+    if (workers % g == 0 && g * block_bytes <= 64e6) best = g;
+  return best < m_blocks ? best : (m_blocks > 0 ? m_blocks : 1);
 }
 
 Schedule make_chunked_schedule(int M, int N, int chunk_tiles, int d_pitch) {
@@ -108,7 +108,7 @@ Schedule make_chunked_schedule(int M, int N, int chunk_tiles, int d_pitch) {
   s.n_tiles = ceil_div(N, kBN);
   s.chunk_tiles = chunk_tiles < 1 ? 1 : chunk_tiles;
   s.n_chunks = ceil_div(s.n_tiles, s.chunk_tiles);
-  s.group_m = balanced_group_m(s.m_blocks, kBM, d_pitch);
+  s.group_m = balanced_group_m(s.m_blocks, kBM, d_pitch, num_sms());
   s.num_units = s.m_blocks * s.n_chunks;
   return s;
 }
@@ -134,7 +134,7 @@ Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch) {
   s.n_tiles = ceil_div(N, kBN);
   s.chunk_tiles = chunk_tiles < 1 ? 1 : chunk_tiles;
   s.n_chunks = ceil_div(s.n_tiles, s.chunk_tiles);
-  s.group_m = balanced_group_m(s.m_blocks, 2 * kBM, d_pitch);
+  s.group_m = balanced_group_m(s.m_blocks, 2 * kBM, d_pitch, num_sms() / 2);
   if (const char* e = getenv("DEMO_GROUP_M")) s.group_m = atoi(e) > 0 ? atoi(e) : s.group_m;  // experiments
   s.num_units = s.m_blocks * s.n_chunks;
   return s;

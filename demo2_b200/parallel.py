@@ -125,8 +125,9 @@ class CudaEngine:
 
     def launches(self, windows):
         # iota, ranges, band list | 2x prep, gidx, fill records, extract GEMM | thresholds |
-        # count GEMM x windows | per-query AP, reduce   (CUB sort/scan kernels not counted)
-        return 3 + 5 + 1 + windows + 2
+        # (count GEMM, tie resolver, conditional tie-fix GEMM) x windows | per-query AP, reduce
+        # (CUB sort/scan kernels and memsets not counted)
+        return 3 + 5 + 1 + 3 * windows + 2
 
     @staticmethod
     def event():
