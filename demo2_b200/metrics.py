@@ -407,6 +407,27 @@ class R1_mAP_eval():
         self.img_prefixes['NIR'] = nir_prefix
         self.img_prefixes['TIR'] = tir_prefix
 
+    def ranked_results(self, distmat, topk=10, num2vis=100):
+        """The selection step of visualize_ranked_results (utils/metrics.py:273-297) without the
+        plotting: for each of the first ``num2vis`` queries the ``topk`` nearest gallery indices
+        among the gallery items seen by a DIFFERENT camera (:279-280) and their pids (:297).  The
+        same-camera columns are masked on the device and the row top-k kernel replaces the full
+        np.argsort; ties go to the lower gallery index."""
+        from .reranking import topk_rows
+        nq = self.num_query
+        n = min(num2vis, nq)
+        dist = distmat if isinstance(distmat, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(distmat, np.float32))
+        dist = dist[:n].to(_dev()).float()
+        cams = torch.as_tensor(np.asarray(self.camids, dtype=np.int64), device=dist.device)
+        same = cams[nq:].unsqueeze(0) == cams[:n].unsqueeze(1)
+        masked = torch.where(same, torch.full_like(dist, float("inf")), dist)
+        k = min(int(topk), dist.shape[1])
+        idx = topk_rows(masked, k).cpu().numpy()
+        n_ok = (~same).sum(1).cpu().numpy()          # fewer than topk different-camera items: shorter list
+        pids = np.asarray(self.pids)
+        lists = [idx[i, :min(k, int(n_ok[i]))].tolist() for i in range(n)]
+        return lists, [[pids[j + nq] for j in row] for row in lists]
+
     def compute(self):  # called after each epoch
         dev = _dev()
         feats = torch.cat([f.to(dev, non_blocking=True) for f in self.feats], dim=0).float()

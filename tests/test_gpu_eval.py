@@ -203,3 +203,22 @@ def test_evaluator_drop_in(M):
     np.testing.assert_allclose(cmc, g["plain_cmc"], atol=2.5 / 836)
     si = sample_index(*distmat.shape)
     np.testing.assert_allclose(distmat.ravel()[si], g["plain_dist_sample"], rtol=DIST_RTOL, atol=DIST_ATOL)
+
+
+def test_ranked_results_feed_matches_reference_selection(M):
+    """visualize_ranked_results' selection (utils/metrics.py:279-280): per query the gallery sorted by
+    distance, items from the query's camera dropped, first topk."""
+    from demo2_b200 import synth
+    s = synth.make_named("rgbnt201", sigma=5.0, seed=1)
+    ev = M.R1_mAP_eval(s.num_query, feat_norm=True)
+    ev.update((torch.cat([s.qf, s.gf]), np.concatenate([s.q_pids, s.g_pids]),
+               torch.from_numpy(np.concatenate([s.q_camids, s.g_camids])), ["x"] * (2 * 836)))
+    cmc, mAP, distmat, pids, camids, qf, gf = ev.compute()
+    lists, lpids = ev.ranked_results(distmat, topk=10)
+    assert len(lists) == 100
+    nq = s.num_query
+    for i in range(100):
+        order = np.argsort(distmat[i], kind="stable")
+        ref = [int(j) for j in order if camids[j + nq] != camids[i]][:10]
+        assert lists[i] == ref
+        assert lpids[i] == [pids[j + nq] for j in ref]
