@@ -2,6 +2,7 @@
 #include "../../include/demo_b200.h"
 
 #include "gemm_epilogues.cuh"
+#include "gemm2_sm100.cuh"
 #include "simt.cuh"
 
 using namespace demo;
@@ -99,8 +100,14 @@ int demo_sqdist_f32(const float* q, const float* g, int Q, int G, int d, int64_t
   ep.M = Q;
   ep.mode = mode;
   ep.rowmax_key = rowmax ? w.rowmax_keys : nullptr;
-  const Schedule s = make_dense_schedule(Q, G);
-  DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+  if (prefer_pair_kernel(Q, G)) {
+    DEMO_TRY(make_gemm2_operands(w.a, w.b, &ops));
+    const Schedule s = make_dense_schedule2(Q, G);
+    DEMO_TRY(launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream));
+  } else {
+    const Schedule s = make_dense_schedule(Q, G);
+    DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+  }
   if (rowmax) {
     keys_to_float_kernel<<<ceil_div(Q, 256), 256, 0, stream>>>(w.rowmax_keys, rowmax, Q);
     DEMO_CHECK_CUDA(cudaGetLastError());

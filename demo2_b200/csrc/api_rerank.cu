@@ -1,5 +1,6 @@
 // extern "C" entry points for re-ranking and top-k (include/demo_b200.h).
 #include "gemm_epilogues.cuh"
+#include "gemm2_sm100.cuh"
 #include "rerank.cuh"
 
 using namespace demo;
@@ -113,8 +114,14 @@ int demo_rerank_shard_topk(const float* feat, int N, int Q, int d, int64_t ld, i
   ep.M = nrows;
   ep.mode = DIST_SQ;
   ep.rowmax_key = w.rowmax_key;
-  const Schedule s = make_dense_schedule(nrows, N);
-  DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+  if (prefer_pair_kernel(nrows, N)) {
+    DEMO_TRY(make_gemm2_operands(rows, w.a, &ops));
+    const Schedule s = make_dense_schedule2(nrows, N);
+    DEMO_TRY(launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream));
+  } else {
+    const Schedule s = make_dense_schedule(nrows, N);
+    DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+  }
   keys_to_float_kernel2<<<ceil_div(nrows, 256), 256, 0, stream>>>(w.rowmax_key, w.rowmax, nrows);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return launch_topk_rows(w.E, N, nrows, N, w.rowmax, rerank_k(k1, k2), rank_rows, nullptr, stream);
@@ -197,8 +204,14 @@ int demo_rerank(const float* feat, int N, int Q, int d, int64_t ld, int flags, i
     ep.M = N;
     ep.mode = DIST_SQ;
     ep.rowmax_key = fused_max ? w.rowmax_key : nullptr;
-    const Schedule s = make_dense_schedule(N, N);
-    DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+    if (prefer_pair_kernel(N, N)) {
+      DEMO_TRY(make_gemm2_operands(w.a, w.a, &ops));
+      const Schedule s = make_dense_schedule2(N, N);
+      DEMO_TRY(launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream));
+    } else {
+      const Schedule s = make_dense_schedule(N, N);
+      DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+    }
     if (fused_max) {
       keys_to_float_kernel2<<<ceil_div(N, 256), 256, 0, stream>>>(w.rowmax_key, w.rowmax, N);
     } else {

@@ -269,6 +269,8 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 // Operands for the CTA-pair kernel: all four tensor maps use 128-row boxes.
 int make_gemm2_operands(const PrepView& a, const PrepView& b, GemmOperands* ops);
 Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch);
+Schedule make_dense_schedule2(int M, int N);
+bool prefer_pair_kernel(int M, int N);
 int max_active_pairs(const void* kernel, int smem);
 
 template <class Epi>

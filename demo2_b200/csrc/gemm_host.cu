@@ -85,6 +85,22 @@ Schedule make_dense_schedule(int M, int N) {
   return s;
 }
 
+// Dense raster for the CTA-pair kernel (256-row blocks).
+Schedule make_dense_schedule2(int M, int N) {
+  Schedule s = make_dense_schedule(M, N);
+  s.m_block_rows = 2 * kBM;
+  s.m_blocks = ceil_div(M, 2 * kBM);
+  s.num_units = s.m_blocks * s.n_tiles;
+  return s;
+}
+
+// The pair kernel pays off once there is enough work to fill the machine with 256 x 256 tiles.
+bool prefer_pair_kernel(int M, int N) {
+  static const bool force_1cta = getenv("DEMO_STORE_1CTA") != nullptr;  // A/B timing experiments
+  return !force_1cta && M > kBM &&
+         static_cast<long long>(ceil_div(M, 2 * kBM)) * ceil_div(N, kBN) >= num_sms() / 2;
+}
+
 // How many row blocks of A share a gallery chunk back to back.  The persistent workers (CTAs or
 // CTA pairs) take consecutive units, so in one "round" they cover group_m A blocks x
 // (workers / group_m) B chunks -- an L2-level super-tile.  group_m divides the worker count so

@@ -66,7 +66,7 @@ __device__ __forceinline__ WorkUnit schedule_get(const Schedule& s, int u) {
     const int g = u / per_group, r = u - g * per_group;
     const int n_in = min(s.group_n, s.n_tiles - g * s.group_n);
     const int m = r / n_in, n = g * s.group_n + (r - m * n_in);
-    w.m0 = m * kBM;
+    w.m0 = m * s.m_block_rows;
     w.n0 = n * kBN;
     w.n_rows = min(kBN, s.N - w.n0);
   } else if (s.mode == 1) {
