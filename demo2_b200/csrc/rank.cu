@@ -198,24 +198,46 @@ __device__ __forceinline__ bool lex_before(float da, int ga, float db, int gb) {
   return da < db || (da == db && ga < gb);
 }
 
-// One warp per query: rank-by-counting of its same-pid records.
-__global__ void build_thresholds_kernel(const int* __restrict__ rec_ofs, const float* __restrict__ rec_dist,
-                                        const int* __restrict__ rec_gidx, const int* __restrict__ rec_junk,
-                                        int Q, int* __restrict__ thr_cnt, float* __restrict__ thr_val,
-                                        int* __restrict__ thr_gidx, int* __restrict__ thr_junk) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One warp per query: rank-by-counting of its same-pid records.  Up to kThrStage records are staged
+// in shared memory first (the O(n^2) comparisons then read warp-wide broadcasts instead of
+// global memory); longer lists fall back to global reads.
+constexpr int kThrWarps = 4;
+constexpr int kThrStage = 256;
+
+__global__ void __launch_bounds__(kThrWarps * 32)
+build_thresholds_kernel(const int* __restrict__ rec_ofs, const float* __restrict__ rec_dist,
+                        const int* __restrict__ rec_gidx, const int* __restrict__ rec_junk,
+                        int Q, int* __restrict__ thr_cnt, float* __restrict__ thr_val,
+                        int* __restrict__ thr_gidx, int* __restrict__ thr_junk) {
+  __shared__ float s_d[kThrWarps][kThrStage];
+  __shared__ int s_g[kThrWarps][kThrStage];
+  __shared__ int s_j[kThrWarps][kThrStage];
+  const int w = threadIdx.x >> 5;
+  const int i = blockIdx.x * kThrWarps + w;
   const int lane = threadIdx.x & 31;
   if (i >= Q) return;
   const int s0 = rec_ofs[i], n = rec_ofs[i + 1] - s0;
+  const bool staged = n <= kThrStage;
+  if (staged) {
+    for (int a = lane; a < n; a += 32) {
+      s_d[w][a] = rec_dist[s0 + a];
+      s_g[w][a] = rec_gidx[s0 + a];
+      s_j[w][a] = rec_junk[s0 + a];
+    }
+    __syncwarp();
+  }
+  const float* d = staged ? s_d[w] : rec_dist + s0;
+  const int* g = staged ? s_g[w] : rec_gidx + s0;
+  const int* jk = staged ? s_j[w] : rec_junk + s0;
   int npos = 0;
   for (int a = lane; a < n; a += 32) {
-    if (rec_junk[s0 + a]) continue;
-    const float da = rec_dist[s0 + a];
-    const int ga = rec_gidx[s0 + a];
+    if (jk[a]) continue;
+    const float da = d[a];
+    const int ga = g[a];
     int pos_before = 0, junk_before = 0;
     for (int b = 0; b < n; ++b) {
-      const bool before = lex_before(rec_dist[s0 + b], rec_gidx[s0 + b], da, ga);
-      const int jb = rec_junk[s0 + b];
+      const bool before = lex_before(d[b], g[b], da, ga);
+      const int jb = jk[b];
       pos_before += (before && !jb) ? 1 : 0;
       junk_before += (before && jb) ? 1 : 0;
     }
@@ -251,7 +273,7 @@ int launch_build_thresholds(const int* rec_ofs, const float* rec_dist, const int
                             const int* rec_junk, int Q, int* thr_cnt, float* thr_val, int* thr_gidx,
                             int* thr_junk, cudaStream_t stream) {
   if (Q <= 0) return DEMO_OK;
-  build_thresholds_kernel<<<ceil_div(Q * 32, 256), 256, 0, stream>>>(rec_ofs, rec_dist, rec_gidx, rec_junk, Q,
+  build_thresholds_kernel<<<ceil_div(Q, kThrWarps), kThrWarps * 32, 0, stream>>>(rec_ofs, rec_dist, rec_gidx, rec_junk, Q,
                                                                      thr_cnt, thr_val, thr_gidx, thr_junk);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
@@ -271,7 +293,7 @@ __global__ void __launch_bounds__(kCmThreads)
 count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
                     const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
                     const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
-                    const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int window) {
+                    const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int window, int skip_small) {
   __shared__ float s_thr[kCmWin];
   __shared__ int s_tg[kCmWin];
   __shared__ unsigned s_hist[kCmWin + 8];
@@ -281,6 +303,8 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
   const int tbase = thr_ofs[i] + window * kCmWin;
   const int nthr = max(0, min(kCmWin, thr_cnt[i] - window * kCmWin));
   if (nthr == 0) return;
+  // rows with <= 63 finite thresholds belong to count_matrix63_kernel
+  if (skip_small && thr_cnt[i] <= 63 && isfinite(thr_val[thr_ofs[i] + thr_cnt[i] - 1])) return;
   for (int k = t; k < nthr; k += kCmThreads) {
     s_thr[k] = thr_val[tbase + k];
     s_tg[k] = thr_gidx[tbase + k];
@@ -339,6 +363,140 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
   }
 }
 
+// Fast path for rows with at most 63 finite thresholds (the common case): the technique of the
+// GEMM count epilogue on a materialised row.  The thresholds are uniform over the block, so the
+// top three levels of the bisection live in registers and the lower three are read from a small
+// table.  Table layout (floats): [0] = -inf sentinel, [1 + k] = t_k for k < 32, [33] = copy of
+// t_31, [34 + (k - 32)] = t_k for k >= 32: the one-word shift of the upper half makes every tree
+// level touch distinct banks (or the same word), and the word below any slot is the threshold
+// below it (tie probe).  The search carries the byte address of the slot; each thread owns a
+// private column of the [64][256] histogram -- no atomics; float4 row loads; 4 B per pair read once.
+constexpr int kCfThreads = 256;
+constexpr int kCfWin = 63;
+
+__global__ void __launch_bounds__(kCfThreads)
+count_matrix63_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
+                      const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
+                      const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
+                      const int* __restrict__ thr_gidx, unsigned* __restrict__ counts) {
+  extern __shared__ unsigned short s_hist[];    // [64][kCfThreads] u16, column = thread (G <= 2^24 per launch)
+  __shared__ float s_tab[68];
+  __shared__ int s_tg[64];
+  __shared__ unsigned s_tot[64];
+  const int i = blockIdx.x, t = threadIdx.x;
+  const int nthr = thr_cnt[i];
+  if (nthr <= 0 || nthr > kCfWin) return;       // larger rows: count_matrix_kernel
+  const int tbase = thr_ofs[i];
+  if (!isfinite(__ldg(thr_val + tbase + nthr - 1))) return;
+  if (t < 64) {
+    const float v = t < nthr ? __ldg(thr_val + tbase + t) : INFINITY;
+    s_tab[t < 32 ? 1 + t : 2 + t] = v;
+    if (t == 31) s_tab[33] = v;
+    if (t == 0) s_tab[0] = -INFINITY;
+    s_tg[t] = t < nthr ? __ldg(thr_gidx + tbase + t) : -1;
+  }
+#pragma unroll 8
+  for (int b = 0; b < 64; ++b) s_hist[b * kCfThreads + t] = 0;
+  __syncthreads();
+  const float t31 = s_tab[32], t15 = s_tab[16], t47 = s_tab[49];
+  const float t7 = s_tab[8], t23 = s_tab[24], t39 = s_tab[41], t55 = s_tab[57];
+  const uint32_t tab0 = smem_u32(s_tab) + 4;    // address of slot 0
+  const uint32_t hist0 = smem_u32(s_hist) + 2 * t;
+  const float* row = distmat + static_cast<long long>(q_perm[i]) * ld;
+
+  // byte address of slot b = #{thresholds <= d}
+  auto search = [&](float d) -> uint32_t {
+    const bool p1 = t31 <= d;
+    uint32_t a = p1 ? tab0 + 33 * 4 : tab0;
+    const float u2 = p1 ? t47 : t15;
+    const bool p2 = u2 <= d;
+    a += p2 ? 64 : 0;
+    const float hi3 = p2 ? t55 : t39, lo3 = p2 ? t23 : t7;
+    a += ((p1 ? hi3 : lo3) <= d) ? 32 : 0;
+    float u;
+    asm("ld.shared.f32 %0, [%1+12];" : "=f"(u) : "r"(a));
+    a += (u <= d) ? 16 : 0;
+    asm("ld.shared.f32 %0, [%1+4];" : "=f"(u) : "r"(a));
+    a += (u <= d) ? 8 : 0;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(u) : "r"(a));
+    a += (u <= d) ? 4 : 0;
+    return a;
+  };
+  auto bump = [&](uint32_t a, float d, int g) {
+    int b = static_cast<int>(a - tab0) >> 2;
+    b -= b > 32 ? 1 : 0;                         // undo the one-word shift of the upper half
+    float below;
+    asm("ld.shared.f32 %0, [%1+-4];" : "=f"(below) : "r"(a));
+    if (below == d) {                            // bit-equal to a threshold: (distance, index) order
+      const int gi = g_index_base + g;
+      while (b > 0 && s_tab[b <= 32 ? b : b + 1] == d && s_tg[b - 1] > gi) --b;
+    }
+    const uint32_t h = hist0 + static_cast<uint32_t>(b) * (kCfThreads * 2);
+    unsigned c;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c) : "r"(h));
+    c += 1u;
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(h), "r"(c));
+  };
+
+  // head up to the first 16-byte aligned element, float4 body (8 independent searches in flight), scalar tail
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(row) >> 2) & 3u);
+  const int head = min(G, (4 - mis) & 3);
+  if (t < head) {
+    const float d = __ldg(row + t);
+    bump(search(d), d, t);
+  }
+  const int nvec = (G - head) >> 2;
+  const float4* row4 = reinterpret_cast<const float4*>(row + head);
+  int v = t;
+  for (; v + kCfThreads < nvec; v += 2 * kCfThreads) {
+    const float4 x = __ldcs(row4 + v), y = __ldcs(row4 + v + kCfThreads);
+    const float d[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    uint32_t a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = search(d[e]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bump(a[e], d[e], head + 4 * (v + (e >> 2) * kCfThreads) + (e & 3));
+  }
+  for (; v < nvec; v += kCfThreads) {
+    const float4 x = __ldcs(row4 + v);
+    const float d[4] = {x.x, x.y, x.z, x.w};
+    uint32_t a[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a[e] = search(d[e]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bump(a[e], d[e], head + 4 * v + e);
+  }
+  const int tail0 = head + 4 * nvec;
+  if (tail0 + t < G) {
+    const float d = __ldg(row + tail0 + t);
+    bump(search(d), d, tail0 + t);
+  }
+  __syncthreads();
+  // bucket totals: warp w sums buckets 8w .. 8w+7 over the 256 columns
+  const int warp = t >> 5, lane = t & 31;
+  for (int b = warp * 8; b < warp * 8 + 8; ++b) {
+    unsigned sum = 0;
+#pragma unroll
+    for (int c = lane; c < kCfThreads; c += 32) sum += s_hist[b * kCfThreads + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_tot[b] = sum;
+  }
+  __syncthreads();
+  if (t < 32) {                                  // counts[k] += sum_{b <= k} tot[b]
+    unsigned a = s_tot[2 * t], c = s_tot[2 * t + 1];
+    unsigned incl = a + c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (t >= o) incl += x;
+    }
+    const unsigned before = incl - a - c;
+    if (2 * t < nthr && before + a) atomicAdd(counts + tbase + 2 * t, before + a);
+    if (2 * t + 1 < nthr && incl) atomicAdd(counts + tbase + 2 * t + 1, incl);
+  }
+}
+
 }  // namespace
 
 int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_base, const int* q_perm,
@@ -346,10 +504,23 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
                         unsigned* counts, int Q, int max_cnt, cudaStream_t stream) {
   if (Q <= 0 || G <= 0) return DEMO_OK;
   static_assert(kCmWin == kCmThreads * 8, "scan layout");
+  // rows with <= 63 finite thresholds: private-histogram kernel; the others: generic windows
+  constexpr int smem = 64 * kCfThreads * 2;
+  static bool configured = false;
+  if (!configured) {
+    DEMO_CHECK_CUDA(cudaFuncSetAttribute(count_matrix63_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const bool fast = G <= (1 << 24);   // u16 private counters: at most G / 256 increments per thread
+  if (fast) {
+    count_matrix63_kernel<<<Q, kCfThreads, smem, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
+                                                          thr_val, thr_gidx, counts);
+    DEMO_CHECK_CUDA(cudaGetLastError());
+  }
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kCmWin);
   for (int w = 0; w < windows; ++w) {
     count_matrix_kernel<<<Q, kCmThreads, 0, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
-                                                      thr_val, thr_gidx, counts, w);
+                                                      thr_val, thr_gidx, counts, w, fast ? 1 : 0);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
   return DEMO_OK;
