@@ -222,3 +222,20 @@ def test_ranked_results_feed_matches_reference_selection(M):
         ref = [int(j) for j in order if camids[j + nq] != camids[i]][:10]
         assert lists[i] == ref
         assert lpids[i] == [pids[j + nq] for j in ref]
+
+
+@pytest.mark.parametrize("Q,G,d", [(100, 700, 64), (129, 300, 100), (257, 1000, 1536), (640, 131, 520)])
+def test_fused_eval_small_and_ragged_shapes(M, Q, G, d):
+    """Both count kernels (one CTA per tile for <= 128 queries, CTA pairs above), ragged row /
+    column / feature counts: fused counts == oracle on our own distance matrix, bit for bit."""
+    rng = np.random.default_rng(Q + G)
+    qf = rng.standard_normal((Q, d)).astype(np.float32)
+    gf = rng.standard_normal((G, d)).astype(np.float32)
+    gf[::7] = qf[rng.integers(0, Q, len(gf[::7]))]          # exact duplicates of queries
+    qp, gp = rng.integers(0, 9, Q), rng.integers(0, 9, G)
+    qc, gc = rng.integers(0, 3, Q), rng.integers(0, 3, G)
+    res = M.evaluate_features(qf, gf, qp, gp, qc, gc, normalize=True)
+    ours = M.sqdist_device(qf, gf, normalize=True).cpu().numpy()
+    ap_o, first_o = _oracle_per_query(ours, qp, gp, qc, gc)
+    np.testing.assert_array_equal(res.first.cpu().numpy(), first_o)
+    np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
