@@ -379,3 +379,73 @@ class ShardedReranker:
             if hi > lo:
                 out[lo:hi] = pieces[r][:hi - lo]
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Evaluation under DDP: every rank keeps the features IT extracted
+# ------------------------------------------------------------------------------------------------
+class DistributedR1mAP:
+    """R1_mAP_eval for a validation set that was split over the ranks (a DistributedSampler on the
+    val loader) instead of being evaluated on rank 0 alone (engine/processor.py:146-148).
+
+    ``update((feat, pid, camid, index))`` takes what each rank extracted plus the dataset index of
+    every sample; samples with ``index < num_query`` are queries (the reference's split,
+    utils/metrics.py:347-353).  ``compute()`` all-gathers the (few) query features and labels,
+    keeps every rank's gallery features where they are -- they become that rank's gallery shard --
+    and runs the gallery-sharded rank-count evaluation.  Ties are broken by rank-major gallery
+    order (the reference's own tie order is unspecified).  Returns (cmc, mAP) identical on all
+    ranks."""
+
+    def __init__(self, num_query, world: int = 1, rank: int = 0, group=None, max_rank=50, feat_norm=True,
+                 engine=None):
+        self.num_query, self.max_rank, self.feat_norm = num_query, max_rank, feat_norm
+        self.world, self.rank, self.group = world, rank, group
+        self.evaluator = ShardedEvaluator(world=world, rank=rank, group=group, engine=engine)
+        self.reset()
+
+    def reset(self):
+        self.feats, self.pids, self.camids, self.index = [], [], [], []
+
+    def update(self, output):
+        feat, pid, camid, index = output
+        self.feats.append(feat.detach())
+        self.pids.extend(np.asarray(pid).tolist())
+        self.camids.extend(np.asarray(camid.cpu() if isinstance(camid, torch.Tensor) else camid).tolist())
+        self.index.extend(np.asarray(index.cpu() if isinstance(index, torch.Tensor) else index).tolist())
+
+    def _gather_var(self, t: torch.Tensor):
+        """all-gather of tensors whose first dimension differs per rank (padded to the maximum)."""
+        import torch.distributed as dist
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(s.item()) for s in sizes]
+        pad = torch.zeros((max(sizes),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(out, pad, group=self.group)
+        return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0), sizes
+
+    def compute(self):
+        feats = torch.cat(self.feats, dim=0).float()
+        dev = feats.device
+        pids = torch.as_tensor(self.pids, dtype=torch.int64, device=dev)
+        cams = torch.as_tensor(self.camids, dtype=torch.int64, device=dev)
+        idx = torch.as_tensor(self.index, dtype=torch.int64, device=dev)
+        is_q = idx < self.num_query
+        qf, q_lab = feats[is_q], torch.stack([idx[is_q], pids[is_q], cams[is_q]], dim=1)
+        gf, g_pid, g_cam = feats[~is_q], pids[~is_q], cams[~is_q]
+        g_base = 0
+        if self.world > 1:
+            qf, _ = self._gather_var(qf)
+            q_lab, _ = self._gather_var(q_lab)
+            _, g_sizes = self._gather_var(torch.zeros((gf.shape[0], 1), dtype=torch.int64, device=dev))
+            g_base = int(sum(g_sizes[:self.rank]))
+        order = torch.argsort(q_lab[:, 0])                 # dataset order of the queries on every rank
+        qf, q_lab = qf[order], q_lab[order]
+        res = self.evaluator.evaluate(qf, gf, q_lab[:, 1].to(torch.int32), g_pid.to(torch.int32),
+                                      q_lab[:, 2].to(torch.int32), g_cam.to(torch.int32), g_index_base=g_base,
+                                      normalize=bool(self.feat_norm), max_rank=self.max_rank)
+        assert res.num_valid > 0, "Error: all query identities do not appear in gallery"
+        self.last_result = res
+        return res.cmc, res.mAP
