@@ -1,6 +1,9 @@
 """Timing experiment: count-GEMM stage of the full-size evaluation (20k x 1M, d=1536), a few
-iterations, prints the per-stage CUDA-event times.  Env DEMO_DEBUG_NOEPI / DEMO_DEBUG_EPI select
-debug epilogue variants (timing only, results are garbage).   python tools/exp_count.py [Q G d iters]"""
+iterations, prints the per-stage CUDA-event times and the SM clocks sampled meanwhile.  Tuning /
+diagnostic switches of the library (read once per process): DEMO_DEBUG_NOEPI=1 mainloop only
+(results are garbage), DEMO_COUNT_1CTA=1 one CTA per tile instead of CTA pairs, DEMO_GROUP_M /
+DEMO_CHUNK_TILES / DEMO_PAIRS unit grouping, DEMO_DEBUG_TIES=1 prints the tie-list fill.
+    python tools/exp_count.py [Q G d iters]"""
 import os
 import sys
 
@@ -39,8 +42,8 @@ for it in range(iters + 2):
         out.append({k: v[0].elapsed_time(v[1]) for k, v in t.items() if isinstance(v, tuple)})
 clk = sampler.stop()
 keys = out[0].keys()
-print("variant NOEPI=%s EPI=%s  Q=%d G=%d d=%d  mAP %.5f" % (os.environ.get("DEMO_DEBUG_NOEPI"),
-                                                            os.environ.get("DEMO_DEBUG_EPI"), Q, G, d, res.mAP))
+print("NOEPI=%s 1CTA=%s  Q=%d G=%d d=%d  mAP %.5f" % (os.environ.get("DEMO_DEBUG_NOEPI"),
+                                                     os.environ.get("DEMO_COUNT_1CTA"), Q, G, d, res.mAP))
 print("  " + "  ".join("%s %.2f" % (k, float(np.mean([o[k] for o in out]))) for k in keys))
 cm = float(np.mean([o["count"] for o in out]))
 print("  clocks", clk)
