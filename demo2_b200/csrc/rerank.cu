@@ -16,6 +16,8 @@
 // fp16 stores, numpy's "compute in float32, round once" half arithmetic.
 #include "rerank.cuh"
 
+#include <cmath>
+
 #include <cub/device/device_scan.cuh>
 
 namespace demo {
@@ -123,7 +125,7 @@ __device__ void bitonic_sort_u64(unsigned long long* s, int n2) {
 template <bool kCached>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const float* __restrict__ row_div, int k,
-                 int* __restrict__ idx_out, float* __restrict__ val_out) {
+                 int* __restrict__ idx_out, float* __restrict__ val_out, int prefix) {
   extern __shared__ unsigned s_dyn[];
   __shared__ unsigned s_hist[256];
   __shared__ unsigned s_prefix, s_need, s_nless, s_neq, s_ncand, s_bound;
@@ -143,15 +145,20 @@ topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const fl
   // 8-byte vector loads when the row allows it (row start 8-byte aligned)
   const bool vec2 = !kCached && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
   const int cols2 = vec2 ? (cols >> 1) : 0;
+  // The bound only needs a subset of the row (the k-th smallest of ANY >= k entries bounds the
+  // k-th smallest of all): long un-cached rows derive it from a prefix, so that most of the row is
+  // read from HBM once (the filter pass) instead of twice.
+  const int pre = kCached ? cols : min(cols, prefix);
+  const int pre2 = vec2 ? (pre >> 1) : 0;
   if (vec2) {
     const float2* src2 = reinterpret_cast<const float2*>(src);
 #pragma unroll 4
-    for (int j = t; j < cols2; j += kTopkThreads) {
+    for (int j = t; j < pre2; j += kTopkThreads) {
       const float2 v = __ldg(src2 + j);
       tmin = min(tmin, min(float_key(v.x + 0.f), float_key(v.y + 0.f)));
     }
   }
-  for (int j = 2 * cols2 + t; j < cols; j += kTopkThreads) {
+  for (int j = 2 * pre2 + t; j < pre; j += kTopkThreads) {
     const unsigned raw = float_key(__ldg(src + j) + 0.f);
     if (kCached) s_raw[j] = raw;
     tmin = min(tmin, raw);
@@ -552,9 +559,18 @@ int launch_topk_rows(const float* mat, long long ld, int rows, int cols, const f
       DEMO_CHECK_CUDA(cudaFuncSetAttribute(topk_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
-    topk_rows_kernel<true><<<rows, kTopkThreads, smem, stream>>>(mat, ld, cols, row_div, k, idx_out, val_out);
+    topk_rows_kernel<true><<<rows, kTopkThreads, smem, stream>>>(mat, ld, cols, row_div, k, idx_out, val_out, cols);
   } else {
-    topk_rows_kernel<false><<<rows, kTopkThreads, 0, stream>>>(mat, ld, cols, row_div, k, idx_out, val_out);
+    // prefix for the bound: the expected number of candidates of the filter pass is about
+    // (cols / prefix) * 64 * ln(64 / (64 - k)) (k-th smallest of 64 group minima); keep it near
+    // half the candidate buffer.  k > 63 uses 256 single-thread groups and the whole row.
+    int prefix = cols;
+    if (k < 64 && cols > 32768) {
+      const double want = static_cast<double>(cols) * 64.0 * log(64.0 / (64.0 - k)) / (kTopkCap / 2);
+      prefix = static_cast<int>(want < 32768.0 ? 32768.0 : (want > cols ? cols : want));
+      prefix &= ~1023;
+    }
+    topk_rows_kernel<false><<<rows, kTopkThreads, 0, stream>>>(mat, ld, cols, row_div, k, idx_out, val_out, prefix);
   }
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;

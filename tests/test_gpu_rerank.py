@@ -133,3 +133,18 @@ def test_row_sharded_reranking_is_bit_identical(shape, k1, k2, ranks):
     sharded = parallel.ShardedReranker().re_ranking(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda(), k1, k2,
                                                     0.3, emulate_ranks=ranks)
     assert torch.equal(whole, sharded)
+
+
+@pytest.mark.parametrize("cols,k", [(100000, 21), (100000, 50), (70001, 63), (100000, 100), (40000, 5)])
+def test_topk_long_rows(cols, k):
+    """Rows longer than the shared-memory cache: the selection bound comes from a row prefix and
+    the row is filtered in one pass; result == stable argsort prefix, including heavy ties."""
+    from demo2_b200 import reranking
+    rng = np.random.default_rng(cols + k)
+    m = rng.random((24, cols), dtype=np.float32)
+    m[3] = np.round(m[3] * 50) / 50            # 51 distinct values: massive ties -> radix fallback
+    m[5, :30000] += 1.0                        # the prefix holds only large values: loose bound
+    m[7] = np.sort(m[7])[::-1]                 # the smallest entries sit at the very end
+    idx = reranking.topk_rows(torch.from_numpy(m).cuda(), k).cpu().numpy()
+    ref = np.argsort(m, axis=1, kind="stable")[:, :k]
+    np.testing.assert_array_equal(idx, ref)
