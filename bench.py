@@ -438,6 +438,17 @@ def other_workloads(dev):
     ms_f, _ = timed(fwd, iters=20)
     ms_fb, _ = timed(fwd_bwd, iters=20)
     res["triplet_3x128x768"] = {"fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "anchors_per_s_fwd": 384 / ms_f * 1e3}
+    # context for the roofline: the library bf16 GEMM on the benchmark's own shape (K = 1536,
+    # 20 000 rows against a 131 072-row slice of the gallery, bf16 output written), long enough to
+    # run into the power cap like the count GEMM does
+    M, N, K = 20000, 131072, 1536
+    a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ms, _ = timed(lambda: torch.matmul(a, b.t(), out=out), iters=150, warm=20)
+    res["cublas_bf16_same_shape"] = {"ms": ms, "tflops": 2.0 * M * N * K / ms * 1e-9, "shape": [M, N, K],
+                                     "note": "one pass; the count GEMM executes three fp16 passes of this shape "
+                                             "(compare with roofline.executed_tflops)"}
     return res
 
 
