@@ -564,10 +564,12 @@ int launch_topk_rows(const float* mat, long long ld, int rows, int cols, const f
     // prefix for the bound: the expected number of candidates of the filter pass is about
     // (cols / prefix) * 64 * ln(64 / (64 - k)) (k-th smallest of 64 group minima); keep it near
     // half the candidate buffer.  k > 63 uses 256 single-thread groups and the whole row.
+    // Rows up to ~12k columns are re-read from L2 by the filter pass (8 resident blocks per SM keep
+    // < 64 MB in flight); beyond that the second pass would come from HBM again.
     int prefix = cols;
-    if (k < 64 && cols > 32768) {
+    if (k < 64 && cols > 12288) {
       const double want = static_cast<double>(cols) * 64.0 * log(64.0 / (64.0 - k)) / (kTopkCap / 2);
-      prefix = static_cast<int>(want < 32768.0 ? 32768.0 : (want > cols ? cols : want));
+      prefix = static_cast<int>(want < 8192.0 ? 8192.0 : (want > cols ? cols : want));
       prefix &= ~1023;
     }
     topk_rows_kernel<false><<<rows, kTopkThreads, 0, stream>>>(mat, ld, cols, row_div, k, idx_out, val_out, prefix);
