@@ -487,9 +487,17 @@ __global__ void inv_fill_kernel(const int* __restrict__ idx, const __half* __res
 }
 
 // ---------------------------------------------------------------------------------------
-// Jaccard distance + blend (one block per query row)
+// Jaccard distance + blend (one block per query row).
+// temp_min[t] receives, for ascending columns j of V[i], fp16(temp_min[t] + min(V[i,j], V[t,j]))
+// (:89-93), so the columns are applied one after another with a block barrier in between (a row
+// may be hit by different threads in consecutive columns).  What used to make a column cost a
+// microsecond were three dependent global loads (V[i] entry -> inverted-list range -> entries):
+// the column metadata is now staged in shared memory per chunk and the entries of 8 columns are
+// fetched together before they are applied in order.
 // ---------------------------------------------------------------------------------------
 constexpr int kJcThreads = 256;
+constexpr int kJcChunk = 512;   // columns staged per round
+constexpr int kJcGroup = 8;     // columns whose entries are fetched together
 
 __global__ void __launch_bounds__(kJcThreads)
 jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ rowmax, int N, int Q,
@@ -498,32 +506,78 @@ jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restri
                float one_minus_lambda_h, float lambda_f, __half* __restrict__ scratch, float* __restrict__ out,
                long long ldo, int row0) {
   extern __shared__ __half s_tmin[];
+  __shared__ int s_beg[kJcChunk], s_end[kJcChunk];
+  __shared__ float s_v[kJcChunk];
   const int li = blockIdx.x, i = li + row0, t = threadIdx.x;   // E / rowmax / scratch / out: local rows
   __half* tmin = scratch ? scratch + (long long)li * N : s_tmin;
   for (int j = t; j < N; j += kJcThreads) tmin[j] = __float2half_rn(0.f);
-  __syncthreads();
   const int c = cnt[i];
-  for (int p = 0; p < c; ++p) {  // ascending column order (:89-93)
-    const __half vij = val[(long long)i * cap + p];
-    if (__half2float(vij) == 0.f) continue;  // block-uniform
-    const int col = idx[(long long)i * cap + p];
-    const int s = inv_ofs[col], e = inv_ofs[col + 1];
-    for (int q = s + t; q < e; q += kJcThreads) {
-      const int r = inv_row[q];
-      const __half m = __float2half_rn(fminf(__half2float(vij), __half2float(inv_val[q])));
-      tmin[r] = np_hadd(tmin[r], m);
+  for (int p0 = 0; p0 < c; p0 += kJcChunk) {
+    __syncthreads();  // tmin initialised / previous chunk consumed
+    const int np = min(kJcChunk, c - p0);
+    for (int p = t; p < np; p += kJcThreads) {
+      const int col = idx[(long long)i * cap + p0 + p];
+      s_v[p] = __half2float(val[(long long)i * cap + p0 + p]);   // 0 -> column skipped (V != 0 test, :88)
+      s_beg[p] = inv_ofs[col];
+      s_end[p] = inv_ofs[col + 1];
     }
     __syncthreads();
+    // columns in groups of kJcGroup: every thread first fetches its entry of each column of the
+    // group (independent loads, one L2 latency for the whole group), then the columns are applied
+    // in order
+    for (int p8 = 0; p8 < np; p8 += kJcGroup) {
+      int er[kJcGroup];
+      float ev[kJcGroup];
+#pragma unroll
+      for (int u = 0; u < kJcGroup; ++u) {
+        const int p = p8 + u;
+        er[u] = -1;
+        ev[u] = 0.f;
+        if (p < np && s_beg[p] + t < s_end[p]) {
+          er[u] = __ldg(inv_row + s_beg[p] + t);
+          ev[u] = __half2float(inv_val[s_beg[p] + t]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kJcGroup; ++u) {  // ascending column order (:89-93)
+        const int p = p8 + u;
+        if (p >= np) break;
+        const float vij = s_v[p];
+        if (vij == 0.f) continue;  // block-uniform
+        if (er[u] >= 0) tmin[er[u]] = np_hadd(tmin[er[u]], __float2half_rn(fminf(vij, ev[u])));
+        for (int q = s_beg[p] + kJcThreads + t; q < s_end[p]; q += kJcThreads) {  // lists longer than one entry per thread
+          const int r = __ldg(inv_row + q);
+          tmin[r] = np_hadd(tmin[r], __float2half_rn(fminf(vij, __half2float(inv_val[q]))));
+        }
+        __syncthreads();
+      }
+    }
   }
+  __syncthreads();
   const __half one = __float2half_rn(1.f), two = __float2half_rn(2.f);
   const __half w = __float2half_rn(one_minus_lambda_h);
   const float div = rowmax[li];
   const int G = N - Q;
-  for (int g = t; g < G; g += kJcThreads) {
-    const __half tm = tmin[Q + g];
-    const __half jac = np_hsub(one, np_hdiv(tm, np_hsub(two, tm)));           // 1 - tmin / (2 - tmin)
-    const float od = E[(long long)li * lde + Q + g] / div;
-    out[(long long)li * ldo + g] = __fadd_rn(__half2float(np_hmul(jac, w)), __fmul_rn(od, lambda_f));  // (:95), no FMA contraction
+  // 8 independent row loads in flight per thread: with 64 KB of temp_min per block only three blocks
+  // fit an SM, so the memory-level parallelism has to come from the thread
+  const float* erow = E + (long long)li * lde + Q;
+  float* orow = out + (long long)li * ldo;
+  for (int g0 = t; g0 < G; g0 += 8 * kJcThreads) {
+    float e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + u * kJcThreads;
+      e[u] = g < G ? __ldcs(erow + g) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + u * kJcThreads;
+      if (g >= G) break;
+      const __half tm = tmin[Q + g];
+      const __half jac = np_hsub(one, np_hdiv(tm, np_hsub(two, tm)));           // 1 - tmin / (2 - tmin)
+      const float od = e[u] / div;
+      __stcs(orow + g, __fadd_rn(__half2float(np_hmul(jac, w)), __fmul_rn(od, lambda_f)));  // (:95), no FMA contraction
+    }
   }
 }
 
