@@ -416,6 +416,7 @@ krecip_kernel(const float* __restrict__ E, long long lde, const float* __restric
 // local query expansion: V_qe[i] = fp16(mean_m V[rank[i][m]]), m < k2 (one block per row)
 // ---------------------------------------------------------------------------------------
 constexpr int kQeThreads = 128;
+constexpr int kQeStage = 4096;   // staged neighbour-row entries (k2 rows of V)
 
 __global__ void __launch_bounds__(kQeThreads)
 expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const int* __restrict__ v_idx,
@@ -427,15 +428,34 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
   int* s_list = reinterpret_cast<int*>(s_dyn + words);  // [capq]
   __shared__ unsigned s_scan[kQeThreads + 1];
   __shared__ int s_nb[64];
+  __shared__ int s_off[65];                 // start of every neighbour's row in the staging buffers
+  __shared__ int s_si[kQeStage];            // the k2 neighbour rows (indices / weights): the merge below
+  __shared__ __half s_sv[kQeStage];         // searches them k2 times per output column
   const int i = blockIdx.x + row0, t = threadIdx.x;
   for (int w = t; w < words; w += kQeThreads) bm[w] = 0;
-  if (t < k2) s_nb[t] = rank[(long long)i * K + t];
+  if (t < k2) {
+    s_nb[t] = rank[(long long)i * K + t];
+    s_off[t + 1] = v_cnt[s_nb[t]];
+  }
   __syncthreads();
+  if (t == 0) {
+    s_off[0] = 0;
+    for (int m = 0; m < k2; ++m) s_off[m + 1] += s_off[m];
+  }
+  __syncthreads();
+  const bool staged = s_off[k2] <= kQeStage;   // otherwise (huge k1) the rows are searched in global memory
   for (int m = 0; m < k2; ++m) {
     const int r = s_nb[m];
-    const int cnt = v_cnt[r];
-    for (int p = t; p < cnt; p += kQeThreads)
-      if (__half2float(v_val[(long long)r * cap + p]) != 0.f) bm_set(bm, v_idx[(long long)r * cap + p]);
+    const int cnt = s_off[m + 1] - s_off[m];
+    for (int p = t; p < cnt; p += kQeThreads) {
+      const int c = v_idx[(long long)r * cap + p];
+      const __half v = v_val[(long long)r * cap + p];
+      if (staged) {
+        s_si[s_off[m] + p] = c;
+        s_sv[s_off[m] + p] = v;
+      }
+      if (__half2float(v) != 0.f) bm_set(bm, c);
+    }
   }
   __syncthreads();
   const int n = bm_enumerate(bm, words, s_list, capq, s_scan);
@@ -446,13 +466,15 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
     float acc = 0.f;
     for (int m = 0; m < k2; ++m) {  // sequential float32 sum in neighbour order (np.mean over fp16 rows)
       const int r = s_nb[m];
-      const int* ri = v_idx + (long long)r * cap;
-      int lo = 0, hi = v_cnt[r];
+      const int len = s_off[m + 1] - s_off[m];
+      const int* ri = staged ? s_si + s_off[m] : v_idx + (long long)r * cap;
+      int lo = 0, hi = len;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (ri[mid] < col) lo = mid + 1; else hi = mid;
       }
-      if (lo < v_cnt[r] && ri[lo] == col) acc += __half2float(v_val[(long long)r * cap + lo]);
+      if (lo < len && ri[lo] == col)
+        acc += __half2float(staged ? s_sv[s_off[m] + lo] : v_val[(long long)r * cap + lo]);
     }
     q_idx[(long long)i * capq + p] = col;
     q_val[(long long)i * capq + p] = __float2half_rn(acc / inv_k2_den);
