@@ -96,8 +96,8 @@ int demo_rerank_shard_topk(const float* feat, int N, int Q, int d, int64_t ld, i
   if (nrows == 0) return DEMO_OK;
   DEMO_REQUIRE(rank_rows, "rerank shard: null output");
   PrepView rows = w.a;  // the local rows as the A operand
-  rows.hi += static_cast<size_t>(row0) * w.a.pitch;
-  rows.lo += static_cast<size_t>(row0) * w.a.pitch;
+  rows.hi += static_cast<size_t>(row0) * 2 * w.a.pitch;
+  rows.lo += static_cast<size_t>(row0) * 2 * w.a.pitch;
   rows.norm += row0;
   rows.inv_scale += row0;
   rows.rows = nrows;

@@ -97,8 +97,7 @@ struct Gemm2Smem {
 
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const Schedule sched, const int num_k_blocks, const typename Epi::Params ep) {
   constexpr int kStages = Gemm2Smem<Epi>::kStages;
   if (Epi::skip(ep)) return;  // uniform over the grid, before any setup
@@ -117,10 +116,8 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a_hi);
-    tma_prefetch_desc(&tm_a_lo);
-    tma_prefetch_desc(&tm_b_hi);
-    tma_prefetch_desc(&tm_b_lo);
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -157,10 +154,8 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             uint8_t* st = smem + stage * kStageBytes2;
             const uint32_t lbar = leader_full0 + 8u * stage;
             if (leader) mbar_expect_tx(&bar_full[stage], 2 * kStageBytes2);
-            tma_load_2d_cg2(st, &tm_a_hi, lbar, kb * kBK, w.m0 + row_ofs);
-            tma_load_2d_cg2(st + kTileABytes, &tm_a_lo, lbar, kb * kBK, w.m0 + row_ofs);
-            tma_load_2d_cg2(st + 2 * kTileABytes, &tm_b_hi, lbar, kb * kBK, w.n0 + n_off + row_ofs);
-            tma_load_2d_cg2(st + 3 * kTileABytes, &tm_b_lo, lbar, kb * kBK, w.n0 + n_off + row_ofs);
+            tma_load_2d_cg2(st, &tm_a, lbar, kb * 2 * kBK, w.m0 + row_ofs);
+            tma_load_2d_cg2(st + 2 * kTileABytes, &tm_b, lbar, kb * 2 * kBK, w.n0 + n_off + row_ofs);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
@@ -187,10 +182,10 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             mbar_wait(&bar_full[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * kStageBytes2);
-            const uint64_t a_hi = make_kmajor_desc<kBK * 2>(sa);
-            const uint64_t a_lo = make_kmajor_desc<kBK * 2>(sa + kTileABytes);
-            const uint64_t b_hi = make_kmajor_desc<kBK * 2>(sa + 2 * kTileABytes);
-            const uint64_t b_lo = make_kmajor_desc<kBK * 2>(sa + 3 * kTileABytes);
+            const uint64_t a_hi = make_kmajor_desc<128>(sa);
+            const uint64_t a_lo = a_hi + 4;
+            const uint64_t b_hi = make_kmajor_desc<128>(sa + 2 * kTileABytes);
+            const uint64_t b_lo = b_hi + 4;
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);  // +32 B per step
@@ -291,8 +286,7 @@ int launch_sqdist_gemm2(const GemmOperands& ops, const Schedule& sched, int max_
     if (const char* e = getenv("DEMO_PAIRS")) pairs = atoi(e) > 0 && atoi(e) < pairs ? atoi(e) : pairs;  // experiments
   }
   const int grid = 2 * (max_units < pairs ? max_units : pairs);
-  kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo, sched,
-                                               ops.num_k_blocks, ep);
+  kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a, ops.b, sched, ops.num_k_blocks, ep);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }

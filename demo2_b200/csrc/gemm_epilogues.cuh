@@ -216,8 +216,9 @@ struct EpiCountT {
                               // word (low / high u16), so counter b sits at a CONSTANT byte offset
                               // (kWin*512 + 2*half) from threshold b and a warp hits 32 different banks
   int nthr = 0, tbase = 0, par = 0;
-  // top three levels of the search tree live in registers
+  // top four levels of the search tree live in registers
   float t31 = 0, t15 = 0, t47 = 0, t7 = 0, t23 = 0, t39 = 0, t55 = 0;
+  float t3 = 0, t11 = 0, t19 = 0, t27 = 0, t35 = 0, t43 = 0, t51 = 0, t59 = 0;  // level 4
 
   __device__ EpiCountT(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
       : p(p_), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {
@@ -285,6 +286,14 @@ struct EpiCountT {
       t23 = thr[23 * 128];
       t39 = thr[39 * 128];
       t55 = thr[55 * 128];
+      t3 = thr[3 * 128];
+      t11 = thr[11 * 128];
+      t19 = thr[19 * 128];
+      t27 = thr[27 * 128];
+      t35 = thr[35 * 128];
+      t43 = thr[43 * 128];
+      t51 = thr[51 * 128];
+      t59 = thr[59 * 128];
     }
   }
 
@@ -315,23 +324,35 @@ struct EpiCountT {
       for (int j = 0; j < kC; ++j) {
         const float2 cm = col[c * kC + j];
         const float d = fmaf(__uint_as_float(r[j]) * ia, cm.x, na + cm.y);
-        // level 1..3 from registers
+        // level 1..4 from registers (the shared-memory pipe is the scarce resource next to the
+        // tensor cores' operand fetch); `last` tracks the largest threshold <= d (tie detection)
         const bool p1 = t31 <= d;
         uint32_t a = p1 ? thr0 + 32 * kRowBytes : thr0;
+        float last = p1 ? t31 : -INFINITY;
         const float u2 = p1 ? t47 : t15;
         const bool p2 = u2 <= d;
         a += p2 ? 16 * kRowBytes : 0;
+        last = p2 ? u2 : last;
         const float hi3 = p2 ? t55 : t39, lo3 = p2 ? t23 : t7;
         const float u3 = p1 ? hi3 : lo3;
-        a += (u3 <= d) ? 8 * kRowBytes : 0;
-        // level 4..6 from shared memory (immediate offsets, one predicated add per level)
-        a += (lds_f32_off<3 * kRowBytes>(a) <= d) ? 4 * kRowBytes : 0;
-        a += (lds_f32_off<1 * kRowBytes>(a) <= d) ? 2 * kRowBytes : 0;
-        a += (lds_f32_off<0>(a) <= d) ? 1 * kRowBytes : 0;
-        // a = thr0 + b * 512 with b = #{t <= d}; the element ties iff t_{b-1} == d.  For b == 0
-        // the probe reads the word below the threshold table (column metadata): a false hit
-        // only costs a tie-list entry, the resolver compares against the real thresholds.
-        ties |= (lds_f32_off<-kRowBytes>(a) == d) ? (1u << j) : 0u;
+        const bool p3 = u3 <= d;
+        a += p3 ? 8 * kRowBytes : 0;
+        last = p3 ? u3 : last;
+        const float q00 = p3 ? t11 : t3, q01 = p3 ? t27 : t19, q10 = p3 ? t43 : t35, q11 = p3 ? t59 : t51;
+        const float u4 = p1 ? (p2 ? q11 : q10) : (p2 ? q01 : q00);
+        const bool p4 = u4 <= d;
+        a += p4 ? 4 * kRowBytes : 0;
+        last = p4 ? u4 : last;
+        // level 5..6 from shared memory (immediate offsets, one predicated add per level)
+        float u = lds_f32_off<1 * kRowBytes>(a);
+        bool q = u <= d;
+        a += q ? 2 * kRowBytes : 0;
+        last = q ? u : last;
+        u = lds_f32_off<0>(a);
+        q = u <= d;
+        a += q ? 1 * kRowBytes : 0;
+        last = q ? u : last;
+        ties |= (last == d) ? (1u << j) : 0u;
         slot[j] = a;
       }
       if (ties && active) {

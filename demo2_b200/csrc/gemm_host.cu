@@ -49,12 +49,14 @@ int make_operand_tensor_map(CUtensorMap* map, const __half* base, int rows, int 
   }
   DEMO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && pitch % 8 == 0,
                "operand not 16-byte aligned (base %p pitch %d)", (const void*)base, pitch);
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows > 0 ? rows : 1)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch) * sizeof(__half)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  // interleaved hi|lo rows (prep.cuh): 2 * pitch halfs per row, one k-block = 64 halfs = 128 bytes
+  (void)d;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(2 * pitch), static_cast<cuuint64_t>(rows > 0 ? rows : 1)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(2 * pitch) * sizeof(__half)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(2 * kBK), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d d %d pitch %d)", (int)r, rows, d, pitch);
@@ -65,10 +67,8 @@ int make_operand_tensor_map(CUtensorMap* map, const __half* base, int rows, int 
 
 int make_gemm_operands(const PrepView& a, const PrepView& b, GemmOperands* ops) {
   DEMO_REQUIRE(a.d == b.d, "operand feature dims differ (%d vs %d)", a.d, b.d);
-  DEMO_TRY(make_operand_tensor_map(&ops->a_hi, a.hi, a.rows, a.d, a.pitch, kBM));
-  DEMO_TRY(make_operand_tensor_map(&ops->a_lo, a.lo, a.rows, a.d, a.pitch, kBM));
-  DEMO_TRY(make_operand_tensor_map(&ops->b_hi, b.hi, b.rows, b.d, b.pitch, kBN));
-  DEMO_TRY(make_operand_tensor_map(&ops->b_lo, b.lo, b.rows, b.d, b.pitch, kBN));
+  DEMO_TRY(make_operand_tensor_map(&ops->a, a.hi, a.rows, a.d, a.pitch, kBM));
+  DEMO_TRY(make_operand_tensor_map(&ops->b, b.hi, b.rows, b.d, b.pitch, kBN));
   ops->num_k_blocks = ceil_div(a.d, kBK);
   return DEMO_OK;
 }
@@ -131,10 +131,8 @@ Schedule make_chunked_schedule(int M, int N, int chunk_tiles, int d_pitch) {
 
 int make_gemm2_operands(const PrepView& a, const PrepView& b, GemmOperands* ops) {
   DEMO_REQUIRE(a.d == b.d, "operand feature dims differ (%d vs %d)", a.d, b.d);
-  DEMO_TRY(make_operand_tensor_map(&ops->a_hi, a.hi, a.rows, a.d, a.pitch, kBM));
-  DEMO_TRY(make_operand_tensor_map(&ops->a_lo, a.lo, a.rows, a.d, a.pitch, kBM));
-  DEMO_TRY(make_operand_tensor_map(&ops->b_hi, b.hi, b.rows, b.d, b.pitch, kBM));  // each CTA loads half a B tile
-  DEMO_TRY(make_operand_tensor_map(&ops->b_lo, b.lo, b.rows, b.d, b.pitch, kBM));
+  DEMO_TRY(make_operand_tensor_map(&ops->a, a.hi, a.rows, a.d, a.pitch, kBM));
+  DEMO_TRY(make_operand_tensor_map(&ops->b, b.hi, b.rows, b.d, b.pitch, kBM));  // each CTA loads half a B tile
   ops->num_k_blocks = ceil_div(a.d, kBK);
   return DEMO_OK;
 }

@@ -23,7 +23,7 @@ namespace demo {
 
 constexpr int kBM = 128;            // rows of A per tile (TMEM lanes)
 constexpr int kBN = 256;            // rows of B per tile (TMEM columns)
-constexpr int kBK = 32;             // fp16 elements per k-block = 64 B = one SWIZZLE_64B span
+constexpr int kBK = 32;             // k elements per k-block; hi[32] | lo[32] = 128 B = one SWIZZLE_128B span
 constexpr int kUmmaK = 16;          // K per tcgen05.mma (kind::f16)
 constexpr int kTileABytes = kBM * kBK * 2;
 constexpr int kTileBBytes = kBN * kBK * 2;
@@ -148,8 +148,7 @@ struct GemmSmem {
 
 template <class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const Schedule sched, const int num_k_blocks, const typename Epi::Params ep) {
   constexpr int kStages = Epi::kStages;
   if (Epi::skip(ep)) return;  // conditional passes (uniform over the grid, before any setup)
@@ -168,10 +167,8 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a_hi);
-    tma_prefetch_desc(&tm_a_lo);
-    tma_prefetch_desc(&tm_b_hi);
-    tma_prefetch_desc(&tm_b_lo);
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -204,11 +201,9 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             mbar_wait(&bar_empty[stage], phase ^ 1u);
             uint8_t* st = smem + stage * kStageBytes;
             mbar_expect_tx(&bar_full[stage], kStageBytes);
-            tma_load_2d(st, &tm_a_hi, &bar_full[stage], kb * kBK, w.m0);
-            tma_load_2d(st + kTileABytes, &tm_a_lo, &bar_full[stage], kb * kBK, w.m0);
-            tma_load_2d(st + 2 * kTileABytes, &tm_b_hi, &bar_full[stage], kb * kBK, w.n0 + n_off);
-            tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &tm_b_lo, &bar_full[stage], kb * kBK,
-                        w.n0 + n_off);
+            // one 128-byte box row = hi[32] | lo[32] of the k-block (interleaved operands, prep.cuh)
+            tma_load_2d(st, &tm_a, &bar_full[stage], kb * 2 * kBK, w.m0);
+            tma_load_2d(st + 2 * kTileABytes, &tm_b, &bar_full[stage], kb * 2 * kBK, w.n0 + n_off);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
@@ -235,10 +230,11 @@ sqdist_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             mbar_wait(&bar_full[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-            const uint64_t a_hi = make_kmajor_desc<kBK * 2>(sa);
-            const uint64_t a_lo = make_kmajor_desc<kBK * 2>(sa + kTileABytes);
-            const uint64_t b_hi = make_kmajor_desc<kBK * 2>(sa + 2 * kTileABytes);
-            const uint64_t b_lo = make_kmajor_desc<kBK * 2>(sa + 2 * kTileABytes + kTileBBytes);
+            // 128-byte swizzled rows: hi at byte 0, lo at byte 64 of every row
+            const uint64_t a_hi = make_kmajor_desc<128>(sa);
+            const uint64_t a_lo = a_hi + 4;
+            const uint64_t b_hi = make_kmajor_desc<128>(sa + 2 * kTileABytes);
+            const uint64_t b_lo = b_hi + 4;
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);  // +32 B per step
@@ -316,7 +312,7 @@ int make_operand_tensor_map(CUtensorMap* map, const __half* base, int rows, int 
                             int box_rows);
 
 struct GemmOperands {
-  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap a, b;
   int num_k_blocks;
 };
 int make_gemm_operands(const PrepView& a, const PrepView& b, GemmOperands* ops);
@@ -338,8 +334,7 @@ int launch_sqdist_gemm(const GemmOperands& ops, const Schedule& sched, int max_u
     configured = true;
   }
   const int grid = max_units < num_sms() ? max_units : num_sms();
-  kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo, sched,
-                                               ops.num_k_blocks, ep);
+  kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a, ops.b, sched, ops.num_k_blocks, ep);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }

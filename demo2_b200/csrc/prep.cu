@@ -87,8 +87,10 @@ prep_rows_vec_kernel(const float* __restrict__ x, int rows, int d, long long ldx
   const bool do_norm = norm_mode != PREP_NORM_NONE;
   const int e = row_exponent(do_norm ? amax / denom : amax);
   float ss2 = 0.f;
-  uint2* hr = reinterpret_cast<uint2*>(hi + static_cast<long long>(r) * pitch);
-  uint2* lr = reinterpret_cast<uint2*>(lo + static_cast<long long>(r) * pitch);
+  // interleaved layout: element k -> half index 64 * (k / 32) + k % 32 (hi), + 32 (lo); in units of
+  // 4 halfs (uint2): vector kv = k / 4 -> 16 * (kv / 8) + kv % 8 (hi), + 8 (lo)
+  uint2* hr = reinterpret_cast<uint2*>(hi + static_cast<long long>(r) * 2 * pitch);
+  uint2* lr = reinterpret_cast<uint2*>(lo + static_cast<long long>(r) * 2 * pitch);
   float4* xo = xn_out ? reinterpret_cast<float4*>(xn_out + static_cast<long long>(src) * ldxn) : nullptr;
 #pragma unroll
   for (int i = 0; i < kNV; ++i) {
@@ -108,8 +110,9 @@ prep_rows_vec_kernel(const float* __restrict__ x, int rows, int d, long long ldx
     ss2 = fmaf(y.w, y.w, ss2);
     const float s0 = ldexpf(y.x, e), s1 = ldexpf(y.y, e), s2 = ldexpf(y.z, e), s3 = ldexpf(y.w, e);
     const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1), h2 = __float2half_rn(s2), h3 = __float2half_rn(s3);
-    hr[k] = pack_half4(h0, h1, h2, h3);
-    lr[k] = pack_half4(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)),
+    const int kq = 16 * (k >> 3) + (k & 7);
+    hr[kq] = pack_half4(h0, h1, h2, h3);
+    lr[kq] = pack_half4(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)),
                        __float2half_rn(s2 - __half2float(h2)), __float2half_rn(s3 - __half2float(h3)));
   }
   ss2 = warp_sum(ss2);
@@ -149,8 +152,8 @@ prep_rows_kernel(const float* __restrict__ x, int rows, int d, long long ldx, in
 
   // pass 2: normalise, split, accumulate |y|^2
   float ss2 = 0.f;
-  __half* hr = hi + static_cast<long long>(r) * pitch;
-  __half* lr = lo + static_cast<long long>(r) * pitch;
+  __half* hr = hi + static_cast<long long>(r) * 2 * pitch;   // interleaved: see PrepView
+  __half* lr = lo + static_cast<long long>(r) * 2 * pitch;
   for (int k = lane; k < pitch; k += 32) {
     float y = 0.f;
     if (k < d) {
@@ -162,8 +165,9 @@ prep_rows_kernel(const float* __restrict__ x, int rows, int d, long long ldx, in
     const float ys = ldexpf(y, e);
     const __half h = __float2half_rn(ys);
     const __half l = __float2half_rn(ys - __half2float(h));
-    hr[k] = h;
-    lr[k] = l;
+    const int kq = 64 * (k >> 5) + (k & 31);
+    hr[kq] = h;
+    lr[kq] = l;
   }
   ss2 = warp_sum(ss2);
   if (lane == 0) {

@@ -14,8 +14,10 @@ namespace demo {
 
 // View of a prepared operand (device pointers into a caller-owned buffer).
 struct PrepView {
-  __half* hi = nullptr;       // [rows][pitch] fp16
-  __half* lo = nullptr;       // [rows][pitch] fp16
+  // hi and lo are INTERLEAVED per 32-element k-block in one array [rows][2 * pitch] fp16:
+  // row r, k-block kb holds hi[32] | lo[32] = one 128-byte line, fetched by ONE TMA box row.
+  __half* hi = nullptr;       // base of the interleaved array (hi of k-block 0)
+  __half* lo = nullptr;       // hi + 32 (lo of k-block 0); same array
   float* norm = nullptr;      // [rows]  sum x^2 (after the optional normalisation), fp32
   float* inv_scale = nullptr; // [rows]  2^-e
   int rows = 0, d = 0, pitch = 0;
@@ -30,8 +32,8 @@ inline size_t prep_carve(Carver& c, int rows, int d, PrepView* v) {
   t.d = d;
   t.pitch = prep_pitch(d);
   size_t r = static_cast<size_t>(rows > 0 ? rows : 1);
-  t.hi = c.take<__half>(r * t.pitch);
-  t.lo = c.take<__half>(r * t.pitch);
+  t.hi = c.take<__half>(r * 2 * t.pitch);
+  t.lo = t.hi ? t.hi + 32 : nullptr;
   t.norm = c.take<float>(r);
   t.inv_scale = c.take<float>(r);
   if (v) *v = t;
