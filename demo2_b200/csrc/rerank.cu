@@ -418,6 +418,7 @@ krecip_kernel(const float* __restrict__ E, long long lde, const float* __restric
 constexpr int kQeThreads = 128;
 constexpr int kQeStage = 4096;   // staged neighbour-row entries (k2 rows of V)
 
+template <bool kStage>
 __global__ void __launch_bounds__(kQeThreads)
 expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const int* __restrict__ v_idx,
               const __half* __restrict__ v_val, const int* __restrict__ v_cnt, int capq,
@@ -429,8 +430,11 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
   __shared__ unsigned s_scan[kQeThreads + 1];
   __shared__ int s_nb[64];
   __shared__ int s_off[65];                 // start of every neighbour's row in the staging buffers
-  __shared__ int s_si[kQeStage];            // the k2 neighbour rows (indices / weights): the merge below
-  __shared__ __half s_sv[kQeStage];         // searches them k2 times per output column
+  // kStage: the k2 neighbour rows (indices / weights) are staged behind s_list -- the merge below
+  // searches them k2 times per output column.  Pays off for large k2 (15 rows of ~45 entries at the
+  // reference's default); with k2 = 6 the extra shared memory costs more occupancy than it saves.
+  int* s_si = s_list + capq;
+  __half* s_sv = reinterpret_cast<__half*>(s_si + kQeStage);
   const int i = blockIdx.x + row0, t = threadIdx.x;
   for (int w = t; w < words; w += kQeThreads) bm[w] = 0;
   if (t < k2) {
@@ -443,7 +447,7 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
     for (int m = 0; m < k2; ++m) s_off[m + 1] += s_off[m];
   }
   __syncthreads();
-  const bool staged = s_off[k2] <= kQeStage;   // otherwise (huge k1) the rows are searched in global memory
+  const bool staged = kStage && s_off[k2] <= kQeStage;   // otherwise the rows are searched in global memory
   for (int m = 0; m < k2; ++m) {
     const int r = s_nb[m];
     const int cnt = s_off[m + 1] - s_off[m];
@@ -720,12 +724,7 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
   const int* f_cnt = w.v_cnt;
   int f_cap = w.cap;
   if (k2 != 1) {
-    const size_t smem = static_cast<size_t>(words) * 4 + static_cast<size_t>(w.capq) * 4;
-    DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d / k2=%d too large for the expansion kernel", N, k2);
-    DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    expand_kernel<<<N, kQeThreads, smem, stream>>>(w.rank, K, N, k2, w.cap, w.v_idx, w.v_val, w.v_cnt, w.capq, w.q_idx,
-                                                   w.q_val, w.q_cnt, 0);
-    DEMO_CHECK_CUDA(cudaGetLastError());
+    DEMO_TRY(launch_expand_rows(w.rank, N, k1, k2, 0, N, w.v_idx, w.v_val, w.v_cnt, w.q_idx, w.q_val, w.q_cnt, stream));
     f_idx = w.q_idx;
     f_val = w.q_val;
     f_cnt = w.q_cnt;
@@ -777,11 +776,17 @@ int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int
   DEMO_REQUIRE(k2 >= 2 && k2 <= 64 && k2 <= N, "re_ranking: expansion needs 2 <= k2 <= min(N, 64) (k2=%d)", k2);
   if (nrows <= 0) return DEMO_OK;
   const int K = rerank_k(k1, k2), cap = rerank_cap(k1), capq = rerank_capq(N, k1, k2), words = ceil_div(N, 32);
-  const size_t smem = static_cast<size_t>(words) * 4 + static_cast<size_t>(capq) * 4;
+  const bool stage = k2 >= 10;
+  const size_t smem = static_cast<size_t>(words) * 4 + static_cast<size_t>(capq) * 4 + (stage ? kQeStage * 6 : 0);
   DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d / k2=%d too large for the expansion kernel", N, k2);
-  DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  expand_kernel<<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx, q_val,
-                                                     q_cnt, row0);
+  DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (stage)
+    expand_kernel<true><<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx,
+                                                             q_val, q_cnt, row0);
+  else
+    expand_kernel<false><<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx,
+                                                              q_val, q_cnt, row0);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }
