@@ -296,7 +296,8 @@ __device__ __forceinline__ bool bm_get(const unsigned* bm, int x) { return (bm[x
 
 // Enumerate the set bits of bm[0..words) in ascending order into out[] (at most cap), returns
 // the total count.  All threads of the block must call.  s_scan: >= blockDim.x + 1 unsigned.
-__device__ int bm_enumerate(const unsigned* bm, int words, int* out, int cap, unsigned* s_scan) {
+__device__ int bm_enumerate(const unsigned* bm, int words, int* out, int cap, unsigned* s_scan,
+                            unsigned* word_prefix = nullptr) {
   const int t = threadIdx.x, nt = blockDim.x;
   const int per = ceil_div(words, nt);
   const int w0 = min(words, t * per), w1 = min(words, w0 + per);
@@ -311,6 +312,7 @@ __device__ int bm_enumerate(const unsigned* bm, int words, int* out, int cap, un
   unsigned pos = s_scan[t];
   for (int w = w0; w < w1; ++w) {
     unsigned bits = bm[w];
+    if (word_prefix) word_prefix[w] = pos;  // number of set bits before word w (rank queries)
     while (bits) {
       const int b = __ffs(bits) - 1;
       bits &= bits - 1;
@@ -416,9 +418,12 @@ krecip_kernel(const float* __restrict__ E, long long lde, const float* __restric
 // local query expansion: V_qe[i] = fp16(mean_m V[rank[i][m]]), m < k2 (one block per row)
 // ---------------------------------------------------------------------------------------
 constexpr int kQeThreads = 128;
-constexpr int kQeStage = 4096;   // staged neighbour-row entries (k2 rows of V)
 
-template <bool kStage>
+// The union of the k2 neighbour rows is built as a bitmap (= sorted unique columns); the weights are
+// then SCATTERED into their output slot, found by a rank query on the bitmap (per-word prefix +
+// popcount), one neighbour row after the other -- the float32 sums run in neighbour order exactly
+// like np.mean over the fp16 rows, with O(entries) work instead of a binary search per
+// (output column, neighbour).
 __global__ void __launch_bounds__(kQeThreads)
 expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const int* __restrict__ v_idx,
               const __half* __restrict__ v_val, const int* __restrict__ v_cnt, int capq,
@@ -426,62 +431,45 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
   extern __shared__ unsigned s_dyn[];
   const int words = ceil_div(N, 32);
   unsigned* bm = s_dyn;
-  int* s_list = reinterpret_cast<int*>(s_dyn + words);  // [capq]
+  unsigned* wp = s_dyn + words;                                   // [words] set bits before each word
+  int* s_list = reinterpret_cast<int*>(s_dyn + 2 * words);        // [capq]
+  float* s_acc = reinterpret_cast<float*>(s_list + capq);         // [capq]
   __shared__ unsigned s_scan[kQeThreads + 1];
-  __shared__ int s_nb[64];
-  __shared__ int s_off[65];                 // start of every neighbour's row in the staging buffers
-  // kStage: the k2 neighbour rows (indices / weights) are staged behind s_list -- the merge below
-  // searches them k2 times per output column.  Pays off for large k2 (15 rows of ~45 entries at the
-  // reference's default); with k2 = 6 the extra shared memory costs more occupancy than it saves.
-  int* s_si = s_list + capq;
-  __half* s_sv = reinterpret_cast<__half*>(s_si + kQeStage);
+  __shared__ int s_nb[64], s_cnt[64];
   const int i = blockIdx.x + row0, t = threadIdx.x;
   for (int w = t; w < words; w += kQeThreads) bm[w] = 0;
   if (t < k2) {
     s_nb[t] = rank[(long long)i * K + t];
-    s_off[t + 1] = v_cnt[s_nb[t]];
+    s_cnt[t] = v_cnt[s_nb[t]];
   }
   __syncthreads();
-  if (t == 0) {
-    s_off[0] = 0;
-    for (int m = 0; m < k2; ++m) s_off[m + 1] += s_off[m];
-  }
-  __syncthreads();
-  const bool staged = kStage && s_off[k2] <= kQeStage;   // otherwise the rows are searched in global memory
   for (int m = 0; m < k2; ++m) {
     const int r = s_nb[m];
-    const int cnt = s_off[m + 1] - s_off[m];
-    for (int p = t; p < cnt; p += kQeThreads) {
-      const int c = v_idx[(long long)r * cap + p];
-      const __half v = v_val[(long long)r * cap + p];
-      if (staged) {
-        s_si[s_off[m] + p] = c;
-        s_sv[s_off[m] + p] = v;
-      }
-      if (__half2float(v) != 0.f) bm_set(bm, c);
-    }
+    const int cnt = s_cnt[m];
+    for (int p = t; p < cnt; p += kQeThreads)
+      if (__half2float(v_val[(long long)r * cap + p]) != 0.f) bm_set(bm, v_idx[(long long)r * cap + p]);
   }
   __syncthreads();
-  const int n = bm_enumerate(bm, words, s_list, capq, s_scan);
+  const int n = bm_enumerate(bm, words, s_list, capq, s_scan, wp);
   const int nn = min(n, capq);
-  const float inv_k2_den = static_cast<float>(k2);
-  for (int p = t; p < nn; p += kQeThreads) {
-    const int col = s_list[p];
-    float acc = 0.f;
-    for (int m = 0; m < k2; ++m) {  // sequential float32 sum in neighbour order (np.mean over fp16 rows)
-      const int r = s_nb[m];
-      const int len = s_off[m + 1] - s_off[m];
-      const int* ri = staged ? s_si + s_off[m] : v_idx + (long long)r * cap;
-      int lo = 0, hi = len;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (ri[mid] < col) lo = mid + 1; else hi = mid;
-      }
-      if (lo < len && ri[lo] == col)
-        acc += __half2float(staged ? s_sv[s_off[m] + lo] : v_val[(long long)r * cap + lo]);
+  for (int p = t; p < nn; p += kQeThreads) s_acc[p] = 0.f;
+  __syncthreads();
+  for (int m = 0; m < k2; ++m) {  // sequential float32 sum in neighbour order (np.mean over fp16 rows)
+    const int r = s_nb[m];
+    const int cnt = s_cnt[m];
+    for (int p = t; p < cnt; p += kQeThreads) {
+      const float v = __half2float(v_val[(long long)r * cap + p]);
+      if (v == 0.f) continue;
+      const int c = v_idx[(long long)r * cap + p];
+      const unsigned pos = wp[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u));
+      if (pos < static_cast<unsigned>(nn)) s_acc[pos] += v;   // columns of one row are distinct: no conflict
     }
-    q_idx[(long long)i * capq + p] = col;
-    q_val[(long long)i * capq + p] = __float2half_rn(acc / inv_k2_den);
+    __syncthreads();
+  }
+  const float k2f = static_cast<float>(k2);
+  for (int p = t; p < nn; p += kQeThreads) {
+    q_idx[(long long)i * capq + p] = s_list[p];
+    q_val[(long long)i * capq + p] = __float2half_rn(s_acc[p] / k2f);
   }
   if (t == 0) q_cnt[i] = nn;
 }
@@ -776,17 +764,11 @@ int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int
   DEMO_REQUIRE(k2 >= 2 && k2 <= 64 && k2 <= N, "re_ranking: expansion needs 2 <= k2 <= min(N, 64) (k2=%d)", k2);
   if (nrows <= 0) return DEMO_OK;
   const int K = rerank_k(k1, k2), cap = rerank_cap(k1), capq = rerank_capq(N, k1, k2), words = ceil_div(N, 32);
-  const bool stage = k2 >= 10;
-  const size_t smem = static_cast<size_t>(words) * 4 + static_cast<size_t>(capq) * 4 + (stage ? kQeStage * 6 : 0);
+  const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(capq) * 8;
   DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d / k2=%d too large for the expansion kernel", N, k2);
-  DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  if (stage)
-    expand_kernel<true><<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx,
-                                                             q_val, q_cnt, row0);
-  else
-    expand_kernel<false><<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx,
-                                                              q_val, q_cnt, row0);
+  DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  expand_kernel<<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx, q_val,
+                                                     q_cnt, row0);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }
