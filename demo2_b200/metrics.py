@@ -80,6 +80,19 @@ def _ws(nbytes: int) -> torch.Tensor:
     return torch.empty(int(nbytes), dtype=torch.uint8, device=_dev())
 
 
+def to_numpy(t: torch.Tensor) -> np.ndarray:
+    """Device matrix -> numpy (what the reference's functions return) through PINNED host memory:
+    a pageable ``.cpu()`` of the 58.8 MB RGBNT100 matrix takes an order of magnitude longer than
+    the kernels that produced it.  The array owns its pinned block (torch's caching host allocator
+    recycles it once the array is dropped)."""
+    if not t.is_cuda:
+        return t.numpy()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
+
+
 # ------------------------------------------------------------------------------
 # distance matrix
 # ------------------------------------------------------------------------------
@@ -111,13 +124,13 @@ def sqdist_device(qf, gf, mode: int = _lib.DIST_SQ, normalize: bool = False, sim
 
 def euclidean_distance(qf, gf):
     """utils/metrics.py:395-401 -- squared L2 (no clamp, no sqrt), returned as numpy."""
-    return sqdist_device(qf, gf, _lib.DIST_SQ).cpu().numpy()
+    return to_numpy(sqdist_device(qf, gf, _lib.DIST_SQ))
 
 
 def cosine_similarity(qf, gf):
     """q g^T / (|q| |g|^T) as numpy.  Not in the reference's utils/metrics.py (SURVEY.md 0);
     defined as 1 - 2 * cosine_dist (layers/triplet_loss.py:34-48)."""
-    return sqdist_device(qf, gf, _lib.DIST_COS_SIM).cpu().numpy()
+    return to_numpy(sqdist_device(qf, gf, _lib.DIST_COS_SIM))
 
 
 # ------------------------------------------------------------------------------
@@ -367,7 +380,7 @@ class R1_mAP():
         cmc, mAP = eval_func_msrv(dist_dev, np.asarray(self.pids[:nq]), np.asarray(self.pids[nq:]),
                                   np.asarray(self.camids[:nq]), np.asarray(self.camids[nq:]),
                                   np.asarray(self.sceneids[:nq]), np.asarray(self.sceneids[nq:]))
-        return cmc, mAP, dist_dev.cpu().numpy(), self.pids, self.camids, qf, gf
+        return cmc, mAP, to_numpy(dist_dev), self.pids, self.camids, qf, gf
 
 
 class R1_mAP_eval():
@@ -449,13 +462,13 @@ class R1_mAP_eval():
             dist_dev, qf, gf = re_ranking_device(qraw, graw, k1=50, k2=15, lambda_value=0.3, normalize=norm,
                                                  want_normalized=True)
             res = evaluate_matrix(dist_dev, plan=plan)
-            distmat = dist_dev.cpu().numpy()
+            distmat = to_numpy(dist_dev)
         else:
             print('=> Computing DistMat with euclidean_distance')
             if Q * G <= MAX_MATERIALIZE:
                 dist_dev, _, qf, gf = sqdist_device(qraw, graw, _lib.DIST_SQ, normalize=norm, want_normalized=True)
                 res = evaluate_matrix(dist_dev, plan=plan)
-                distmat = dist_dev.cpu().numpy()
+                distmat = to_numpy(dist_dev)
             else:
                 res = evaluate_features(qraw, graw, plan=plan, normalize=norm, want_normalized=True)
                 qf, gf, distmat = res.qn, res.gn, None

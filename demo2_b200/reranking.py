@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .metrics import _dev, _features, _ws
+from .metrics import _dev, _features, _ws, to_numpy
 
 
 def _is_matrix_like(x) -> bool:
@@ -73,15 +73,15 @@ def re_ranking_matrix_device(q_g, q_q, g_g, k1=20, k2=6, lambda_value=0.3):
 def re_ranking(*args, **kwargs):
     """See module docstring: dispatches on the call form (2 feature matrices vs 3 distance blocks)."""
     if len(args) >= 3 and _is_matrix_like(args[2]):
-        return re_ranking_matrix_device(*args, **kwargs).cpu().numpy()
+        return to_numpy(re_ranking_matrix_device(*args, **kwargs))
     names = ["probFea", "galFea", "k1", "k2", "lambda_value", "local_distmat", "only_local"]
     params = dict(zip(names, args))
     params.update(kwargs)
     if "q_g" in params:
-        return re_ranking_matrix_device(**params).cpu().numpy()
-    return re_ranking_device(params["probFea"], params["galFea"], params["k1"], params["k2"],
-                             params["lambda_value"], params.get("local_distmat"),
-                             params.get("only_local", False)).cpu().numpy()
+        return to_numpy(re_ranking_matrix_device(**params))
+    return to_numpy(re_ranking_device(params["probFea"], params["galFea"], params["k1"], params["k2"],
+                                      params["lambda_value"], params.get("local_distmat"),
+                                      params.get("only_local", False)))
 
 
 def topk_rows(mat, k: int, want_values: bool = False):
