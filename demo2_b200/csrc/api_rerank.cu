@@ -136,7 +136,7 @@ int demo_rerank_shard_krecip(int N, int Q, int d, int k1, int k2, int row0, int 
   DEMO_TRY(get_rr_shard(ws, ws_bytes, N, Q, d, k1, k2, rows_cap, &w));
   DEMO_REQUIRE(rank_all && v_idx && v_val && v_cnt, "rerank shard: null pointer");
   return launch_krecip_rows(w.E, N, w.rowmax, rank_all, N, k1, k2, row0, nrows, v_idx, static_cast<__half*>(v_val),
-                            v_cnt, static_cast<cudaStream_t>(stream_));
+                            v_cnt, w.r.rh_idx, w.r.rh_cnt, static_cast<cudaStream_t>(stream_));
 }
 
 // Stage 3: local query expansion of the local rows from the gathered V rows (:73-78).

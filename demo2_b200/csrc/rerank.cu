@@ -331,10 +331,39 @@ __device__ int bm_enumerate(const unsigned* bm, int words, int* out, int cap, un
 constexpr int kKrThreads = 128;
 constexpr int kMaxK = 128;  // k1 + 1 <= kMaxK
 
+// R(c, kh) for EVERY row c, once: the expansion step of every row i asks for the half-size
+// reciprocal sets of its ~k1 candidates, and a row is a candidate of ~k1 other rows -- computing
+// them per (i, c) repeated each reciprocity test ~k1 times.  One warp per row; the list keeps the
+// forward-neighbour order (cf[np.nonzero(cb == cand)], :63-65).
+__global__ void __launch_bounds__(128)
+recip_half_kernel(const int* __restrict__ rank, int K, int N, int kh, int* __restrict__ rh_idx,
+                  int* __restrict__ rh_cnt) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= N) return;
+  const int* rc = rank + (long long)c * K;
+  int n = 0;
+  for (int base = 0; base < kh; base += 32) {
+    const int m = base + lane;
+    bool rec = false;
+    int x = -1;
+    if (m < kh) {
+      x = rc[m];
+      const int* rx = rank + (long long)x * K;
+      for (int mm = 0; mm < kh; ++mm) rec |= rx[mm] == c;
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, rec);
+    if (rec) rh_idx[(long long)c * kh + n + __popc(ball & ((1u << lane) - 1u))] = x;
+    n += __popc(ball);
+  }
+  if (lane == 0) rh_cnt[c] = n;
+}
+
 __global__ void __launch_bounds__(kKrThreads)
 krecip_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ rowmax,
               const int* __restrict__ rank, int K, int N, int k1, int kh, int cap, int* __restrict__ v_idx,
-              __half* __restrict__ v_val, int* __restrict__ v_cnt, int row0) {
+              __half* __restrict__ v_val, int* __restrict__ v_cnt, int row0, const int* __restrict__ rh_idx,
+              const int* __restrict__ rh_cnt) {
   extern __shared__ unsigned s_dyn[];
   const int words = ceil_div(N, 32);
   unsigned* bm_kri = s_dyn;            // reciprocal set R(i, k1)
@@ -372,30 +401,16 @@ krecip_kernel(const float* __restrict__ E, long long lde, const float* __restric
   const int warp = t >> 5, lane = t & 31;
   for (int ci = warp; ci < nkri; ci += kKrThreads / 32) {
     const int c = s_kri[ci];
-    const int* rc = rank + (long long)c * K;
-    int len = 0, inter = 0;
-    unsigned member[kMaxK / 32] = {};  // which of cf[0..kh) are reciprocal, per lane-strided slot
-    for (int base = 0, slot = 0; base < kh; base += 32, ++slot) {
+    const int len = rh_cnt[c];                       // |R(c, k1/2)| (precomputed, recip_half_kernel)
+    const int* rc = rh_idx + (long long)c * kh;
+    int inter = 0;
+    for (int base = 0; base < len; base += 32) {
       const int m = base + lane;
-      bool rec = false;
-      int x = -1;
-      if (m < kh) {
-        x = rc[m];
-        const int* rx = rank + (long long)x * K;
-        for (int mm = 0; mm < kh; ++mm) rec |= rx[mm] == c;
-      }
-      const unsigned ball = __ballot_sync(0xffffffffu, rec);
-      const unsigned ball_in = __ballot_sync(0xffffffffu, rec && bm_get(bm_kri, x));
-      len += __popc(ball);
-      inter += __popc(ball_in);
-      member[slot] = ball;
+      const bool in = m < len && bm_get(bm_kri, rc[m]);
+      inter += __popc(__ballot_sync(0xffffffffu, in));
     }
-    if (static_cast<double>(inter) > (2.0 / 3.0) * static_cast<double>(len)) {
-      for (int base = 0, slot = 0; base < kh; base += 32, ++slot) {
-        const int m = base + lane;
-        if (m < kh && ((member[slot] >> lane) & 1u)) bm_set(bm_exp, rc[m]);
-      }
-    }
+    if (static_cast<double>(inter) > (2.0 / 3.0) * static_cast<double>(len))
+      for (int m = lane; m < len; m += 32) bm_set(bm_exp, rc[m]);
   }
   __syncthreads();
   const int n = bm_enumerate(bm_exp, words, s_list, cap, s_scan);  // np.unique: sorted ascending
@@ -670,6 +685,8 @@ size_t rerank_carve(Carver& c, int N, int Q, int k1, int k2, RerankWs* w) {
   t.v_idx = c.take<int>(n * t.cap);
   t.v_val = c.take<__half>(n * t.cap);
   t.v_cnt = c.take<int>(n);
+  t.rh_idx = c.take<int>(n * rerank_kh(k1));
+  t.rh_cnt = c.take<int>(n);
   t.q_idx = c.take<int>(n * t.capq);
   t.q_val = c.take<__half>(n * t.capq);
   t.q_cnt = c.take<int>(n);
@@ -704,7 +721,9 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
     const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(w.cap) * 8;
     DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d too large for the shared-memory bitmaps", N);
     DEMO_CHECK_CUDA(cudaFuncSetAttribute(krecip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    krecip_kernel<<<N, kKrThreads, smem, stream>>>(E, lde, rowmax, w.rank, K, N, k1, kh, w.cap, w.v_idx, w.v_val, w.v_cnt, 0);
+    recip_half_kernel<<<ceil_div(N * 32, 128), 128, 0, stream>>>(w.rank, K, N, kh, w.rh_idx, w.rh_cnt);
+    krecip_kernel<<<N, kKrThreads, smem, stream>>>(E, lde, rowmax, w.rank, K, N, k1, kh, w.cap, w.v_idx, w.v_val, w.v_cnt, 0,
+                                                   w.rh_idx, w.rh_cnt);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
   const int* f_idx = w.v_idx;
@@ -746,14 +765,18 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
 // between the stages, so every kernel indexes them by global row.
 // ---------------------------------------------------------------------------------------
 int launch_krecip_rows(const float* E, long long lde, const float* rowmax, const int* rank_all, int N, int k1,
-                       int k2, int row0, int nrows, int* v_idx, __half* v_val, int* v_cnt, cudaStream_t stream) {
+                       int k2, int row0, int nrows, int* v_idx, __half* v_val, int* v_cnt, int* rh_idx,
+                       int* rh_cnt, cudaStream_t stream) {
   DEMO_REQUIRE(k1 >= 1 && k1 + 1 <= kMaxK && k1 + 1 <= N, "re_ranking: need 1 <= k1 < min(N, %d) (k1=%d, N=%d)", kMaxK, k1, N);
   if (nrows <= 0) return DEMO_OK;
   const int K = rerank_k(k1, k2), kh = rerank_kh(k1), cap = rerank_cap(k1), words = ceil_div(N, 32);
   const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(cap) * 8;
   DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d too large for the shared-memory bitmaps", N);
   DEMO_CHECK_CUDA(cudaFuncSetAttribute(krecip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  krecip_kernel<<<nrows, kKrThreads, smem, stream>>>(E, lde, rowmax, rank_all, K, N, k1, kh, cap, v_idx, v_val, v_cnt, row0);
+  // every rank needs R(c, k1/2) of all rows (any row can be a candidate of a local row)
+  recip_half_kernel<<<ceil_div(N * 32, 128), 128, 0, stream>>>(rank_all, K, N, kh, rh_idx, rh_cnt);
+  krecip_kernel<<<nrows, kKrThreads, smem, stream>>>(E, lde, rowmax, rank_all, K, N, k1, kh, cap, v_idx, v_val, v_cnt, row0,
+                                                     rh_idx, rh_cnt);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }

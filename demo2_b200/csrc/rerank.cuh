@@ -11,6 +11,8 @@ struct RerankWs {
   int* v_idx = nullptr;      // [N][cap]   V rows before expansion
   __half* v_val = nullptr;
   int* v_cnt = nullptr;      // [N]
+  int* rh_idx = nullptr;     // [N][kh]  R(c, k1/2) of every row (reciprocal half-size sets)
+  int* rh_cnt = nullptr;     // [N]
   int* q_idx = nullptr;      // [N][capq]  V rows after local query expansion
   __half* q_val = nullptr;
   int* q_cnt = nullptr;
@@ -41,7 +43,8 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
 
 // row-sharded stages (see rerank.cu)
 int launch_krecip_rows(const float* E, long long lde, const float* rowmax, const int* rank_all, int N, int k1,
-                       int k2, int row0, int nrows, int* v_idx, __half* v_val, int* v_cnt, cudaStream_t stream);
+                       int k2, int row0, int nrows, int* v_idx, __half* v_val, int* v_cnt, int* rh_idx,
+                       int* rh_cnt, cudaStream_t stream);
 int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int nrows, const int* v_idx,
                        const __half* v_val, const int* v_cnt, int* q_idx, __half* q_val, int* q_cnt,
                        cudaStream_t stream);
