@@ -29,6 +29,8 @@ struct EvalWs {
   double* map;            // [1]
   int* nvalid;            // [1]
   TieList ties;           // exact-tie list of the count GEMM (entries + {count, overflow})
+  unsigned* pace;         // per-iteration arrival counters of the paced CTA-pair schedule
+  size_t pace_cap;
 };
 
 // Capacity of the tie list: every valid positive ties with its own threshold (<= T entries per
@@ -59,7 +61,10 @@ size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w) {
   t.map = c.take<double>(1);
   t.nvalid = c.take<int>(4);
   t.ties.cap = tie_capacity(Q, T);
-  t.ties.hdr = c.take<unsigned>(16);
+  // header of the tie list and, right behind it (one memset), the pacing counters of the pair kernel
+  t.pace_cap = static_cast<size_t>(ceil_div(static_cast<int>(q1), kBM)) * ceil_div(static_cast<int>(g1), kBN) + 64;
+  t.ties.hdr = c.take<unsigned>(16 + t.pace_cap);
+  t.pace = t.ties.hdr + 16;
   t.ties.entries = c.take<int4>(t.ties.cap);
   if (w) *w = t;
   return c.off;
@@ -153,12 +158,28 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
   if (pair) {
     DEMO_TRY(make_gemm2_operands(w.a, w.b, &ops2));
     s2 = make_chunked_schedule2(Q, G, chunk_tiles, w.a.pitch);
+    // Paced schedule (gemm_sm100.cuh, Schedule::pace): a worker starts its i-th unit only when
+    // every worker has issued the loads of its unit i - 2.  Free-running workers drift apart by
+    // more than an L2 lifetime within milliseconds and then each re-fetches the gallery tiles its
+    // group shares from DRAM (20k x 262k: 60 GB -> 17 GB of DRAM reads; at 20k x 1M the kernel
+    // runs 137 ms instead of 148 ms because the saved HBM power raises the capped SM clock).
+    // DEMO_PACE=<window> / DEMO_PACE=-1 (off) and DEMO_PACE_TILES=<tiles per step> are experiments.
+    static const int pace_window = getenv("DEMO_PACE") ? atoi(getenv("DEMO_PACE")) : 1;
+    static const int pace_tiles_env = getenv("DEMO_PACE_TILES") ? atoi(getenv("DEMO_PACE_TILES")) : 0;
+    int pace_tiles = pace_tiles_env > 0 && pace_tiles_env < chunk_tiles ? pace_tiles_env : chunk_tiles;
+    const int pace_steps = ceil_div(chunk_tiles, pace_tiles);
+    if (pace_window >= 0 && static_cast<size_t>(s2.num_units) * pace_steps < w.pace_cap) {
+      s2.pace = w.pace;
+      s2.pace_window = pace_window;
+      s2.pace_tiles = pace_tiles;
+      s2.pace_steps = pace_steps;
+    }
   }
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kWin);
   static const bool no_epi = getenv("DEMO_DEBUG_NOEPI") != nullptr;  // timing experiments only
   for (int wdw = 0; wdw < windows; ++wdw) {
     ep.window = no_epi ? -1 : wdw;
-    DEMO_CHECK_CUDA(cudaMemsetAsync(w.ties.hdr, 0, 16 * sizeof(unsigned), stream));
+    DEMO_CHECK_CUDA(cudaMemsetAsync(w.ties.hdr, 0, (16 + (s2.pace ? static_cast<size_t>(s2.num_units) * s2.pace_steps + 1 : 0)) * sizeof(unsigned), stream));
     if (pair) DEMO_TRY(launch_sqdist_gemm2<EpiCount>(ops2, s2, s2.num_units, ep, stream));
     else DEMO_TRY(launch_sqdist_gemm<EpiCount>(ops, s, s.num_units, ep, stream));
     resolve_ties_kernel<<<2 * num_sms(), 256, 0, stream>>>(w.ties, w.b_gidx, thr_ofs, thr_cnt, thr_val, thr_gidx,

@@ -146,9 +146,19 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const uint32_t leader_full0 = mapa_u32(smem_u32(&bar_full[0]), 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = cid; u < num_units; u += ncl) {
+      int it = 0;
+      for (int u = cid; u < num_units; u += ncl, ++it) {
         const WorkUnit w = schedule_get(sched, u);
-        for (int n_off = 0; n_off < w.n_rows; n_off += kBN) {
+        int t = 0, step = it * sched.pace_steps;
+        for (int n_off = 0; n_off < w.n_rows; n_off += kBN, ++t) {
+          if (sched.pace != nullptr && t % sched.pace_tiles == 0) {
+            const int j = step - 1 - sched.pace_window;
+            if (j >= 0) {
+              const unsigned expect = static_cast<unsigned>(min(ncl, num_units - (j / sched.pace_steps) * ncl));
+              const volatile unsigned* flag = sched.pace + j;
+              while (*flag < expect) __nanosleep(500);
+            }
+          }
           for (int kb = 0; kb < num_k_blocks; ++kb) {
             mbar_wait(&bar_empty[stage], phase ^ 1u);
             uint8_t* st = smem + stage * kStageBytes2;
@@ -161,7 +171,14 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               phase ^= 1u;
             }
           }
+          if (sched.pace != nullptr && (t + 1) % sched.pace_tiles == 0) {
+            if (leader) atomicAdd(sched.pace + step, 1u);
+            ++step;
+          }
         }
+        // short unit (end of a gallery row of chunks): the steps it does not have count as done
+        if (sched.pace != nullptr && leader)
+          for (; step < (it + 1) * sched.pace_steps; ++step) atomicAdd(sched.pace + step, 1u);
       }
     }
   } else if (warp == 1) {

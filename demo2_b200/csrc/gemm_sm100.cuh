@@ -51,6 +51,13 @@ struct Schedule {
   int m_block_rows = kBM;  // A rows per unit (2 * kBM for the CTA-pair kernel)
   int num_units = 0;     // modes 0/1
   const int4* list = nullptr;      // mode 2: (m_block, n0, n_rows, _)
+  // Pacing of the persistent workers (CTA-pair kernel).  A unit is cut into steps of pace_tiles
+  // tiles (pace_steps per unit); pace[i] counts the workers whose producer has issued every load
+  // of its i-th step, and a producer starts step i only when all workers are done with step
+  // i - 1 - pace_window.  Keeps the workers that share a gallery chunk within an L2 lifetime of
+  // each other.  nullptr: free-running.  Zeroed by the caller (num_units * pace_steps entries).
+  unsigned* pace = nullptr;
+  int pace_window = 0, pace_tiles = 1, pace_steps = 1;
   const int* list_count = nullptr; // mode 2: device-side unit count
 };
 

@@ -477,3 +477,57 @@ def triplet_loss_grad(global_feat, labels, margin=None, hard_factor: float = 0.0
             grad[a] += v
             grad[j] -= v
     return grad
+
+
+# --------------------------------------------------------------------------
+# distance-matrix batch losses (layers/cluster_loss.py, layers/range_loss.py)
+# --------------------------------------------------------------------------
+def batch_identities(targets, ordered: bool, ids_per_batch: int, imgs_per_id: int):
+    """cluster_loss.py:44-59 / range_loss.py:103-118: every imgs_per_id-th label of a P x K
+    ordered batch, else the sorted unique labels."""
+    targets = np.asarray(targets)
+    if ordered and targets.shape[0] == ids_per_batch * imgs_per_id:
+        return targets[0:targets.shape[0]:imgs_per_id]
+    return np.unique(targets)
+
+
+def cluster_loss(features, targets, margin=10, ordered=True, ids_per_batch=16, imgs_per_id=4):
+    """cluster_loss.py:33-86, identity by identity as the reference loops.
+    Returns (loss, intra_max_distance [P], inter_min_distance [P])."""
+    x, t = np.asarray(features, F32), np.asarray(targets)
+    labels = batch_identities(t, ordered, ids_per_batch, imgs_per_id)
+    P = labels.shape[0]
+    centers = np.zeros((P, x.shape[1]), F32)
+    intra = np.zeros(P, F32)
+    inter = np.zeros(P, F32)
+    for i in range(P):
+        same = x[t == labels[i]]
+        centers[i] = same.mean(axis=0, dtype=F32)                           # :72-73
+        intra[i] = euclidean_dist(centers[i:i + 1], same).max()            # :74-76
+    for i in range(P):
+        others = np.arange(P) != i
+        inter[i] = euclidean_dist(centers[i:i + 1], centers[others]).min()  # :79-82
+    loss = np.maximum(intra - inter + F32(margin), F32(0)).mean(dtype=F32)  # :85
+    return F32(loss), intra, inter
+
+
+def range_loss(features, targets, k=2, margin=0.1, alpha=0.5, beta=0.5, ordered=True, ids_per_batch=32,
+               imgs_per_id=4):
+    """range_loss.py:38-201 with the reference's own selection rules: the k largest intra-class
+    distances are every second element of the tail of the sorted flattened matrix (:62), the
+    smallest centre distance is element [n] of the sorted centre matrix (:89).
+    Returns (range_loss, intra_class_loss, inter_class_loss)."""
+    x, t = np.asarray(features, F32), np.asarray(targets)
+    labels = batch_identities(t, ordered, ids_per_batch, imgs_per_id)
+    P = labels.shape[0]
+    centers = np.stack([x[t == labels[i]].mean(axis=0, dtype=F32) for i in range(P)])   # :120-130
+    cc = np.sort(euclidean_dist(centers, centers).reshape(-1), kind="stable")
+    inter = np.maximum(F32(margin) - cc[P], F32(0))                          # :89, :147
+    intra = np.zeros(P, F32)
+    for i in range(P):
+        same = x[t == labels[i]]
+        flat = np.sort(euclidean_dist(same, same).reshape(-1), kind="stable")
+        top_k = flat[-k * 2::2]                                              # :62
+        intra[i] = F32(k) / np.sum(F32(1.0) / top_k, dtype=F32)              # :183-184
+    intra_loss = intra.sum(dtype=F32)
+    return F32(F32(alpha) * intra_loss + F32(beta) * inter), F32(intra_loss), F32(inter)

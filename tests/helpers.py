@@ -43,3 +43,28 @@ def sample_index(n_rows: int, n_cols: int, count: int = 4096):
 
 def load_golden(name: str):
     return np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+
+
+# ClusterLoss / RangeLoss fixtures.  P identities x K images, features = spread * centre
+# + noise; `ordered` False shuffles the batch and drops a few samples (ragged identities).
+BATCH_LOSS_CASES = {
+    "pk8x16": dict(P=8, K=16, d=768, seed=11, spread=0.6, ordered=True, k=2, cluster_margin=10, range_margin=0.1),
+    "pk16x4": dict(P=16, K=4, d=2048, seed=12, spread=0.5, ordered=True, k=2, cluster_margin=10, range_margin=60.0),
+    "ragged": dict(P=6, K=9, d=512, seed=13, spread=0.7, ordered=False, k=3, cluster_margin=5, range_margin=25.0),
+}
+
+
+def batch_loss_case(name: str):
+    """(features fp32 [B, d], targets int64 [B]) of a BATCH_LOSS_CASES entry, as CPU torch tensors."""
+    import torch
+    spec = BATCH_LOSS_CASES[name]
+    g = torch.Generator().manual_seed(spec["seed"])
+    P, K, d = spec["P"], spec["K"], spec["d"]
+    centers = torch.randn(P, d, generator=g) * spec["spread"]
+    ids = torch.randperm(100, generator=g)[:P]          # arbitrary, unsorted identity numbers
+    targets = ids.repeat_interleave(K)
+    feats = centers.repeat_interleave(K, dim=0) + torch.randn(P * K, d, generator=g)
+    if not spec["ordered"]:
+        keep = torch.randperm(P * K, generator=g)[:P * K - 5]
+        feats, targets = feats[keep].contiguous(), targets[keep].contiguous()
+    return feats, targets

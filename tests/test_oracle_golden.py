@@ -277,3 +277,22 @@ def test_msrv_oracle_full_shape_and_evaluator():
                                             s.num_query)
     assert abs(mAP - float(g2["mAP"])) < 5e-6
     np.testing.assert_allclose(dist.ravel()[sample_index(*dist.shape)], g2["dist_sample"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["pk8x16", "pk16x4", "ragged"])
+def test_batch_losses_oracle_matches_reference(name):
+    """ClusterLoss / RangeLoss restatements (oracle.cluster_loss / range_loss) against the
+    reference's CPU-torch outputs (layers/cluster_loss.py, layers/range_loss.py)."""
+    from tests.helpers import BATCH_LOSS_CASES, batch_loss_case
+    spec, g = BATCH_LOSS_CASES[name], load_golden("batch_loss_" + name)
+    feats, targets = batch_loss_case(name)
+    x, t = feats.numpy(), targets.numpy()
+    kw = dict(ordered=spec["ordered"], ids_per_batch=spec["P"], imgs_per_id=spec["K"])
+    loss, intra, inter = oracle.cluster_loss(x, t, margin=spec["cluster_margin"], **kw)
+    np.testing.assert_allclose(intra, g["cl_intra"], rtol=1e-5)
+    np.testing.assert_allclose(inter, g["cl_inter"], rtol=1e-5)
+    np.testing.assert_allclose(loss, g["cl_loss"], rtol=1e-5)
+    rl, r_intra, r_inter = oracle.range_loss(x, t, k=spec["k"], margin=spec["range_margin"], **kw)
+    np.testing.assert_allclose(r_intra, g["rl_intra"], rtol=1e-5)
+    np.testing.assert_allclose(r_inter, g["rl_inter"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rl, g["rl_loss"], rtol=1e-5)
