@@ -15,6 +15,7 @@ Prints ONE JSON line (rank 0).
 from __future__ import annotations
 
 import argparse
+import builtins
 import json
 import os
 import subprocess
@@ -482,6 +483,22 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the small-workload timings")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line: libraries that write to file descriptor 1 meanwhile (NCCL
+    # prints its version banner there) are pointed at stderr until the line is due
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _print = builtins.print
+
+    def print_line(*a, **k):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        _print(*a, **k)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
+    global print
+    print = print_line
     if args.impl == "reference":
         run_reference(args)
     else:

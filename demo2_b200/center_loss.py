@@ -5,8 +5,7 @@ close to their own (un-normalised, large-norm) centre, i.e. in the cancellation 
 split-fp16 tensor-core path keeps only ~2e-5 relative accuracy, and the
 matrix is tiny (batch x classes), so the FFMA kernel of the same entry point is used.  The backward pass is analytic: only the B own-class entries carry gradient.
 
-The other distance-matrix losses of that row (``ClusterLoss`` / ``RangeLoss``) are not imported by
-the reference's training path (``layers/make_loss.py:8-10``) and are not provided."""
+The other distance-matrix losses of that row are in ``cluster_loss.py`` and ``range_loss.py``."""
 from __future__ import annotations
 
 import torch
