@@ -2,7 +2,8 @@
 iterations, prints the per-stage CUDA-event times and the SM clocks sampled meanwhile.  Tuning /
 diagnostic switches of the library (read once per process): DEMO_DEBUG_NOEPI=1 mainloop only
 (results are garbage), DEMO_COUNT_1CTA=1 one CTA per tile instead of CTA pairs, DEMO_GROUP_M /
-DEMO_CHUNK_TILES / DEMO_PAIRS unit grouping, DEMO_DEBUG_TIES=1 prints the tie-list fill.
+DEMO_CHUNK_TILES / DEMO_PAIRS unit grouping, DEMO_PACE=<window>|-1 / DEMO_PACE_TILES pacing of the CTA
+pairs, DEMO_DEBUG_TIES=1 prints the tie-list fill.
     python tools/exp_count.py [Q G d iters]"""
 import os
 import sys
