@@ -33,6 +33,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -147,16 +152,29 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      bool paced = sched.pace != nullptr;
       for (int u = cid; u < num_units; u += ncl, ++it) {
         const WorkUnit w = schedule_get(sched, u);
         int t = 0, step = it * sched.pace_steps;
         for (int n_off = 0; n_off < w.n_rows; n_off += kBN, ++t) {
-          if (sched.pace != nullptr && t % sched.pace_tiles == 0) {
+          if (paced && t % sched.pace_tiles == 0) {
             const int j = step - 1 - sched.pace_window;
             if (j >= 0) {
               const unsigned expect = static_cast<unsigned>(min(ncl, num_units - (j / sched.pace_steps) * ncl));
               const volatile unsigned* flag = sched.pace + j;
-              while (*flag < expect) __nanosleep(500);
+              if (*flag < expect) {
+                // Pacing is a performance device, never a correctness dependency: if the others do not
+                // show up within 20 ms (part of the grid not resident yet because another kernel
+                // holds SMs), this worker stops waiting for the rest of the launch.
+                const unsigned long long t0 = globaltimer_ns();
+                while (*flag < expect) {
+                  __nanosleep(500);
+                  if (globaltimer_ns() - t0 > 20000000ull) {
+                    paced = false;
+                    break;
+                  }
+                }
+              }
             }
           }
           for (int kb = 0; kb < num_k_blocks; ++kb) {
