@@ -137,12 +137,28 @@ def cpu_eval_chunk(oracle, qf, gf_n, qp, gp, qc, gc):
     return oracle.eval_func(dist, qp, gp, qc, gc, sort_kind=None)  # the reference's default argsort
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use the host's cores.
+    Returns the BLAS thread count in effect."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores)
+        blas = [p["num_threads"] for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(blas) if blas else torch.get_num_threads()
+    except ImportError:
+        return torch.get_num_threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import reid_oracle as oracle
     import torch
+    blas_threads = use_all_host_threads()
     name = args.workload
     Q, G, d, nid, ncam, sigma = WORKLOADS[name]
     cores = os.cpu_count() or 1
@@ -172,7 +188,7 @@ def run_reference(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_desc(name)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "blas_threads": torch.get_num_threads()},
+                             "blas_threads": blas_threads},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -456,7 +472,7 @@ def other_workloads(dev):
 def cpu_baseline(name, q_host, g_host, q_pid, g_pid, q_cam, g_cam):
     """Oracle port of the reference's compute() on a bounded query sample, host cores."""
     from oracle import reid_oracle as oracle
-    import torch
+    blas_threads = use_all_host_threads()
     G = g_host.shape[0]
     chunk = 128 if G > 100000 else min(q_host.shape[0], 1024)   # ~10-15 s of host work on the large gallery
     qf = q_host[:chunk].numpy()
@@ -467,7 +483,7 @@ def cpu_baseline(name, q_host, g_host, q_pid, g_pid, q_cam, g_cam):
     cpu_eval_chunk(oracle, qf, gf_n, q_pid[:chunk], g_pid, q_cam[:chunk], g_cam)
     dt = time.perf_counter() - t0
     return {"value": chunk / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-            "blas_threads": torch.get_num_threads(),
+            "blas_threads": blas_threads,
             "sample": "%d-query chunk x full %d gallery, %.2f s (gallery normalisation %.2f s not included; sgemm "
                       "multi-threaded, argsort and the per-query loop single-threaded as in the reference)"
                       % (chunk, G, dt, t_norm)}
