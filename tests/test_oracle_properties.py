@@ -1,0 +1,77 @@
+"""Property tests of the oracle's rank-count form, the identity the CUDA
+path and its multi-GPU sharding are built on.  Matrices are drawn from a handful of distinct values,
+so exact ties -- the case the (distance, gallery index) rule exists for -- occur in every example.
+CPU only."""
+from __future__ import annotations
+
+import numpy as np
+from hypothesis import assume, given, settings, strategies as st
+
+from tests.helpers import oracle
+
+
+def _case(seed, num_q, num_g, nid, ncam, levels):
+    rng = np.random.default_rng(seed)
+    dist = rng.integers(0, levels, (num_q, num_g)).astype(np.float32) * np.float32(0.25)
+    return (dist, rng.integers(0, nid, num_q), rng.integers(0, nid, num_g), rng.integers(0, ncam, num_q),
+            rng.integers(0, ncam, num_g))
+
+
+def _brute_counts(dist, qp, gp, qc, gc, lo, hi):
+    """r - 1 and c - 1 restricted to gallery columns [lo, hi), straight from the definition:
+    #{g valid (resp. positive) : (d_g, g) lexicographically before (d_p, p)} for every valid
+    positive p of every query, in (distance, index) order of p."""
+    out_r, out_c = [], []
+    for q in range(dist.shape[0]):
+        junk = (gp == qp[q]) & (gc == qc[q])
+        pos = (gp == qp[q]) & ~junk
+        plist = sorted(np.nonzero(pos)[0], key=lambda p: (dist[q, p], p))
+        for p in plist:
+            g = np.arange(lo, hi)
+            before = (dist[q, g] < dist[q, p]) | ((dist[q, g] == dist[q, p]) & (g < p))
+            out_r.append(int((before & ~junk[g]).sum()))
+            out_c.append(int((before & pos[g]).sum()))
+    return np.asarray(out_r, np.int64), np.asarray(out_c, np.int64)
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), num_q=st.integers(1, 6), num_g=st.integers(1, 24), nid=st.integers(1, 4),
+       ncam=st.integers(1, 3), levels=st.integers(1, 5), cuts=st.lists(st.integers(0, 24), max_size=3))
+def test_rank_counts_are_additive_over_gallery_shards(seed, num_q, num_g, nid, ncam, levels, cuts):
+    dist, qp, gp, qc, gc = _case(seed, num_q, num_g, nid, ncam, levels)
+    ofs, idx, r, c = oracle.rank_counts(dist, qp, gp, qc, gc)
+    bounds = sorted({0, num_g, *[min(x, num_g) for x in cuts]})
+    tot_r = np.zeros(len(r), np.int64)
+    tot_c = np.zeros(len(c), np.int64)
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        pr, pc = _brute_counts(dist, qp, gp, qc, gc, lo, hi)
+        tot_r += pr
+        tot_c += pc
+    np.testing.assert_array_equal(tot_r + 1, r)
+    np.testing.assert_array_equal(tot_c + 1, c)
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), num_q=st.integers(1, 8), num_g=st.integers(1, 40), nid=st.integers(1, 5),
+       ncam=st.integers(1, 3), levels=st.integers(1, 6), max_rank=st.integers(1, 50))
+def test_count_form_equals_sorted_form(seed, num_q, num_g, nid, ncam, levels, max_rank):
+    """cmc_map_from_counts(rank_counts(...)) == eval_func(...) with the stable tie rule, including
+    queries without a valid positive (skipped) and galleries smaller than max_rank.
+
+    Excluded: a scored query that keeps fewer than max_rank gallery items after the junk removal.
+    The reference then appends a SHORTER cmc row (metrics.py:146-149) and np.asarray over rows of
+    different lengths raises (:165) -- or, if all rows happen to be equally short, returns a CMC
+    shorter than max_rank.  The count form (and the CUDA path) always returns min(max_rank, G)
+    entries; real galleries never get there."""
+    dist, qp, gp, qc, gc = _case(seed, num_q, num_g, nid, ncam, levels)
+    ofs, idx, r, c = oracle.rank_counts(dist, qp, gp, qc, gc)
+    assume(ofs[-1] > 0)  # eval_func asserts otherwise (covered by test_eval_edge_cases)
+    eff_rank = min(max_rank, num_g)
+    for q in range(num_q):
+        if ofs[q + 1] > ofs[q]:
+            kept = int((~((gp == qp[q]) & (gc == qc[q]))).sum())
+            assume(kept >= eff_rank)
+    cmc_a, map_a = oracle.eval_func(dist, qp, gp, qc, gc, max_rank=max_rank)
+    cmc_b, map_b = oracle.cmc_map_from_counts(ofs, r, c, max_rank=max_rank, num_gallery=num_g)
+    np.testing.assert_array_equal(cmc_a, cmc_b)
+    assert abs(map_a - map_b) < 1e-12
