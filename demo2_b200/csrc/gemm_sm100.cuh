@@ -48,6 +48,8 @@ struct Schedule {
   int chunk_tiles = 1;   // mode 1: n-tiles per unit
   int n_chunks = 0;      // mode 1
   int group_m = 16;      // mode 1: m-blocks that share a chunk consecutively
+  int adj = 0;           // mode 1: > 1 = that many chunks are in flight per group and the workers that
+                         // share an m-block are neighbours (w, w + 1, ...) instead of w, w + group_m, ...
   int m_block_rows = kBM;  // A rows per unit (2 * kBM for the CTA-pair kernel)
   int num_units = 0;     // modes 0/1
   const int4* list = nullptr;      // mode 2: (m_block, n0, n_rows, _)
@@ -80,7 +82,15 @@ __device__ __forceinline__ WorkUnit schedule_get(const Schedule& s, int u) {
     const int per_group = s.group_m * s.n_chunks;
     const int g = u / per_group, r = u - g * per_group;
     const int m_in = min(s.group_m, s.m_blocks - g * s.group_m);
-    const int c = r / m_in, m = g * s.group_m + (r - c * m_in);
+    int c = r / m_in, m = g * s.group_m + (r - c * m_in);
+    if (s.adj > 1 && m_in == s.group_m) {
+      const int blk_units = s.group_m * s.adj, blk = r / blk_units;
+      if ((blk + 1) * s.adj <= s.n_chunks) {     // full block of adj chunks x group_m m-blocks
+        const int idx = r - blk * blk_units;
+        m = g * s.group_m + idx / s.adj;
+        c = blk * s.adj + idx % s.adj;
+      }
+    }
     w.m0 = m * s.m_block_rows;
     w.n0 = c * s.chunk_tiles * kBN;
     w.n_rows = min(s.chunk_tiles * kBN, s.N - w.n0);
