@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
@@ -46,16 +47,48 @@ const char* last_error();
   } while (0)
 
 constexpr int kNumSMsB200 = 148;
+constexpr int kMaxDevices = 64;
+
+// Per-device caches: the library may be called on several devices of one process (and from
+// several host threads), so nothing device-specific lives in a plain function-static.
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
+// One integer per device, 0 = not computed yet (relaxed atomics: a racing first call computes the
+// same value twice at worst).
+struct PerDeviceInt {
+  std::atomic<int> v[kMaxDevices];
+  PerDeviceInt() {
+    for (auto& x : v) x.store(0, std::memory_order_relaxed);
+  }
+  int get(int dev) const { return v[dev].load(std::memory_order_relaxed); }
+  void set(int dev, int value) { v[dev].store(value, std::memory_order_relaxed); }
+};
 
 inline int num_sms() {
-  static int n = 0;
+  static PerDeviceInt cache;
+  const int dev = current_device();
+  int n = cache.get(dev);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = kNumSMsB200;
+    cache.set(dev, n);
   }
   return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: do it once per
+// (kernel, device).  `once` is a function-static PerDeviceInt at the launch site.
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(PerDeviceInt& once, Kernel kernel, int smem) {
+  const int dev = current_device();
+  if (once.get(dev)) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) once.set(dev, 1);
+  return e;
 }
 
 template <typename T>

@@ -310,15 +310,18 @@ int launch_sqdist_gemm2(const GemmOperands& ops, const Schedule& sched, int max_
   auto kernel = sqdist_gemm2_kernel<Epi>;
   constexpr int smem = Gemm2Smem<Epi>::kTotal;
   static_assert(smem <= 232448, "shared memory budget exceeded");
-  static int pairs = 0;
+  static PerDeviceInt configured, pairs_of;   // per device: shared-memory opt-in, resident CTA pairs
+  const int dev = current_device();
+  DEMO_CHECK_CUDA(ensure_dynamic_smem(configured, kernel, smem));
+  int pairs = pairs_of.get(dev);
   if (!pairs) {
-    DEMO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     pairs = max_active_pairs(reinterpret_cast<const void*>(kernel), smem);
     if (pairs <= 0) {
       set_error("CTA-pair kernel cannot be scheduled on this device");
       return DEMO_ERR_CUDA;
     }
     if (const char* e = getenv("DEMO_PAIRS")) pairs = atoi(e) > 0 && atoi(e) < pairs ? atoi(e) : pairs;  // experiments
+    pairs_of.set(dev, pairs);
   }
   const int grid = 2 * (max_units < pairs ? max_units : pairs);
   kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a, ops.b, sched, ops.num_k_blocks, ep);

@@ -345,11 +345,8 @@ int launch_sqdist_gemm(const GemmOperands& ops, const Schedule& sched, int max_u
   auto kernel = sqdist_gemm_kernel<Epi>;
   constexpr int smem = GemmSmem<Epi>::kTotal;
   static_assert(smem <= 232448, "shared memory budget exceeded");
-  static bool configured = false;
-  if (!configured) {
-    DEMO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static PerDeviceInt configured;
+  DEMO_CHECK_CUDA(ensure_dynamic_smem(configured, kernel, smem));
   const int grid = max_units < num_sms() ? max_units : num_sms();
   kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a, ops.b, sched, ops.num_k_blocks, ep);
   DEMO_CHECK_CUDA(cudaGetLastError());

@@ -506,12 +506,9 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
   static_assert(kCmWin == kCmThreads * 8, "scan layout");
   // rows with <= 63 finite thresholds: private-histogram kernel; the others: generic windows
   constexpr int smem = 64 * kCfThreads * 2;
-  static bool configured = false;
-  if (!configured) {
-    DEMO_CHECK_CUDA(cudaFuncSetAttribute(count_matrix63_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  const bool fast = G <= (1 << 24);   // u16 private counters: at most G / 256 increments per thread
+  static PerDeviceInt configured;
+  DEMO_CHECK_CUDA(ensure_dynamic_smem(configured, count_matrix63_kernel, smem));
+  const bool fast = G < (1 << 24) - 512;   // u16 private counters: at most G / 256 (+ head / tail) increments per thread
   if (fast) {
     count_matrix63_kernel<<<Q, kCfThreads, smem, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
                                                           thr_val, thr_gidx, counts);

@@ -640,11 +640,8 @@ int launch_topk_rows(const float* mat, long long ld, int rows, int cols, const f
   // which keeps 8 blocks resident per SM instead of 4 and hides the load latency better.
   const size_t smem = static_cast<size_t>(cols) * 4;
   if (smem <= 16 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      DEMO_CHECK_CUDA(cudaFuncSetAttribute(topk_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
+    static PerDeviceInt configured;
+    DEMO_CHECK_CUDA(ensure_dynamic_smem(configured, topk_rows_kernel<true>, 200 * 1024));
     topk_rows_kernel<true><<<rows, kTopkThreads, smem, stream>>>(mat, ld, cols, row_div, k, idx_out, val_out, cols);
   } else {
     // prefix for the bound: the expected number of candidates of the filter pass is about

@@ -5,7 +5,7 @@ CPU only."""
 from __future__ import annotations
 
 import numpy as np
-from hypothesis import assume, given, settings, strategies as st
+from hypothesis import HealthCheck, assume, given, settings, strategies as st
 
 from tests.helpers import oracle
 
@@ -34,7 +34,8 @@ def _brute_counts(dist, qp, gp, qc, gc, lo, hi):
     return np.asarray(out_r, np.int64), np.asarray(out_c, np.int64)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True, database=None,
+          suppress_health_check=[HealthCheck.filter_too_much, HealthCheck.too_slow])
 @given(seed=st.integers(0, 2 ** 31 - 1), num_q=st.integers(1, 6), num_g=st.integers(1, 24), nid=st.integers(1, 4),
        ncam=st.integers(1, 3), levels=st.integers(1, 5), cuts=st.lists(st.integers(0, 24), max_size=3))
 def test_rank_counts_are_additive_over_gallery_shards(seed, num_q, num_g, nid, ncam, levels, cuts):
@@ -51,7 +52,8 @@ def test_rank_counts_are_additive_over_gallery_shards(seed, num_q, num_g, nid, n
     np.testing.assert_array_equal(tot_c + 1, c)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True, database=None,
+          suppress_health_check=[HealthCheck.filter_too_much, HealthCheck.too_slow])
 @given(seed=st.integers(0, 2 ** 31 - 1), num_q=st.integers(1, 8), num_g=st.integers(1, 40), nid=st.integers(1, 5),
        ncam=st.integers(1, 3), levels=st.integers(1, 6), max_rank=st.integers(1, 50))
 def test_count_form_equals_sorted_form(seed, num_q, num_g, nid, ncam, levels, max_rank):
