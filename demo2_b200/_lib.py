@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdemo_b200.so")
 
 # flags (mirror include/demo_b200.h)
 DIST_SQ, DIST_SQRT, DIST_COS_SIM, DIST_COS_DIST = 0, 1, 2, 3
-FLAG_L2NORM, FLAG_TRIPLET_NORM, FLAG_SIMT = 0x10, 0x20, 0x40
+FLAG_L2NORM, FLAG_TRIPLET_NORM, FLAG_SIMT, FLAG_HOST_INPUT = 0x10, 0x20, 0x40, 0x80
 
 c_f32p = C.POINTER(C.c_float)
 c_f64p = C.POINTER(C.c_double)
@@ -33,8 +33,13 @@ SIGNATURES = {
     "demo_plan_bytes": (sz, [i32, i32]),
     "demo_eval_plan": (i32, [vp, vp, i32, i32, vp, sz, c_i64p, vp]),
     "demo_plan_pointers": (i32, [vp, sz, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "demo_plan_info": (i32, [vp, sz, i32, i32, C.POINTER(vp)]),
     "demo_eval_workspace_bytes": (sz, [i32, i32, i32, i64]),
+    "demo_eval_workspace_bytes_ex": (sz, [i32, i32, i32, i64, i32]),
     "demo_eval_matrix_workspace_bytes": (sz, [i32, i32, i64]),
+    "demo_eval_prepare": (i32, [vp, i32, i32, i64, i32, i32, i32, i32, vp, sz, i32, i32, i64, vp, sz, vp, vp]),
+    "demo_eval_extract": (i32, [i32, i32, i32, vp, vp, i32, vp, vp, sz, i64, vp, sz, vp, vp, vp, vp]),
+    "demo_eval_count_range": (i32, [i32, i32, i32, i64, vp, sz, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "demo_eval_records": (i32, [vp, vp, i32, i32, i32, i64, i64, i32, vp, vp, i32, vp, sz, i64, vp, sz,
                                 vp, vp, vp, vp, vp, vp]),
     "demo_build_thresholds": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
@@ -59,6 +64,16 @@ SIGNATURES = {
     "demo_triplet_hard_fwd": (i32, [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "demo_triplet_hard_bwd": (i32, [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "demo_hard_example_mining": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "demo_comm_available": (i32, []),
+    "demo_comm_nccl_version": (i32, []),
+    "demo_comm_unique_id": (i32, [vp]),
+    "demo_comm_init": (i32, [i32, i32, vp]),
+    "demo_comm_destroy": (i32, []),
+    "demo_comm_info": (i32, [c_i32p, c_i32p]),
+    "demo_comm_check": (i32, []),
+    "demo_comm_all_gather": (i32, [vp, vp, sz, vp]),
+    "demo_comm_all_reduce_sum_u32": (i32, [vp, sz, vp]),
+    "demo_comm_broadcast": (i32, [vp, sz, i32, vp]),
 }
 
 _lib = None

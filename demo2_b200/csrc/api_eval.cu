@@ -31,7 +31,13 @@ struct EvalWs {
   TieList ties;           // exact-tie list of the count GEMM (entries + {count, overflow})
   unsigned* pace;         // per-iteration arrival counters of the paced CTA-pair schedule
   size_t pace_cap;
+  unsigned char* blk_flag;  // [ceil(Q/256)] query blocks with a row of more than kWin thresholds (slab path)
+  float* slab;            // [kSlabRows][slab_ld] distance slab of the flagged query blocks; nullptr = not carved
+  int slab_ld;
 };
+
+constexpr int kSlabRows = 256;        // one CTA-pair block of queries
+constexpr int kSlabMaxCols = 1 << 20; // gallery columns per slab pass (1 GB of fp32 at most)
 
 // Capacity of the tie list: every valid positive ties with its own threshold (<= T entries per
 // window) plus coincidental bit-equal distances; beyond it the exact tie-fix pass takes over.
@@ -40,7 +46,8 @@ inline unsigned tie_capacity(int Q, long long T) {
   return static_cast<unsigned>(c < (1ll << 27) ? c : (1ll << 27));
 }
 
-size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w) {
+// max_cnt > kWin adds the distance slab (LAST, so every other offset is independent of it).
+size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w, int max_cnt = 0) {
   EvalWs t;
   const size_t t1 = T > 0 ? static_cast<size_t>(T) : 1, q1 = Q > 0 ? Q : 1, g1 = G > 0 ? G : 1;
   prep_carve(c, Q, d, &t.a);
@@ -66,13 +73,21 @@ size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w) {
   t.ties.hdr = c.take<unsigned>(16 + t.pace_cap);
   t.pace = t.ties.hdr + 16;
   t.ties.entries = c.take<int4>(t.ties.cap);
+  t.blk_flag = c.take<unsigned char>(ceil_div(static_cast<int>(q1), 256) + 16);
+  t.slab = nullptr;
+  t.slab_ld = 0;
+  if (max_cnt > kWin) {
+    t.slab_ld = static_cast<int>(round_up(g1 < static_cast<size_t>(kSlabMaxCols) ? g1 : static_cast<size_t>(kSlabMaxCols), size_t(4)));
+    t.slab = c.take<float>(static_cast<size_t>(kSlabRows) * t.slab_ld);
+  }
   if (w) *w = t;
   return c.off;
 }
 
-__global__ void gidx_kernel(const int* __restrict__ g_perm, int G, int base, int* __restrict__ out) {
+__global__ void gidx_kernel(const int* __restrict__ g_perm, int G, int base, const int* __restrict__ g_index,
+                            int* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < G) out[i] = base + g_perm[i];
+  if (i < G) out[i] = g_index ? g_index[g_perm[i]] : base + g_perm[i];
 }
 
 // Adds the lexicographic tie corrections recorded by the count GEMM:
@@ -104,7 +119,14 @@ int get_plan(const void* plan, size_t plan_bytes, int Q, int G, PlanView* p) {
   return DEMO_OK;
 }
 
-int get_ws(void* ws, size_t ws_bytes, int Q, int G, int d, long long T, EvalWs* w) {
+// max_cnt > kWin: the slab is used when the caller's workspace has room for it
+// (demo_eval_workspace_bytes_ex); otherwise w->slab stays nullptr (window passes instead).
+int get_ws(void* ws, size_t ws_bytes, int Q, int G, int d, long long T, EvalWs* w, int max_cnt = 0) {
+  if (max_cnt > kWin) {
+    Carver cs(ws, ws_bytes);
+    carve_eval(cs, Q, G, d, T, w, max_cnt);
+    if (ws && cs.ok()) return DEMO_OK;
+  }
   Carver c(ws, ws_bytes);
   carve_eval(c, Q, G, d, T, w);
   if (!ws || !c.ok()) {
@@ -120,16 +142,81 @@ int norm_mode_of(int flags) {
   return PREP_NORM_NONE;
 }
 
-int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int* thr_cnt, const float* thr_val,
-                   const int* thr_gidx, unsigned* counts, int max_cnt, int chunk_tiles, cudaStream_t stream) {
+PrepView sub_rows(const PrepView& v, int row0, int nrows) {
+  PrepView s = v;
+  s.hi = v.hi + static_cast<long long>(row0) * 2 * v.pitch;
+  s.lo = s.hi + 32;
+  s.norm = v.norm + row0;
+  s.inv_scale = v.inv_scale + row0;
+  s.rows = nrows;
+  return s;
+}
+
+// Slab path for the query blocks flagged in w.blk_flag (a row with more than kWin thresholds):
+// per 256-row block the distances against the gallery range are stored once (EpiStore; the launch
+// is a no-op for unflagged blocks) and counted by the streaming kernels of rank.cu, whatever the
+// number of thresholds -- one GEMM pass plus 4 B per pair of HBM traffic instead of one full GEMM
+// per 63 thresholds.
+int count_slabs(const EvalWs& w, int Q, const PrepView& b, const int* b_gidx, const int* thr_ofs, const int* thr_cnt,
+                const float* thr_val, const int* thr_gidx, unsigned* counts, int max_cnt, cudaStream_t stream) {
+  for (int m0 = 0; m0 < Q; m0 += kSlabRows) {
+    const int rows = Q - m0 < kSlabRows ? Q - m0 : kSlabRows;
+    const PrepView a = sub_rows(w.a, m0, rows);
+    for (int c0 = 0; c0 < b.rows; c0 += w.slab_ld) {
+      const int cols = b.rows - c0 < w.slab_ld ? b.rows - c0 : w.slab_ld;
+      const PrepView bc = sub_rows(b, c0, cols);
+      EpiStore::Params ep;
+      ep.a_norm = a.norm;
+      ep.a_inv = a.inv_scale;
+      ep.b_norm = bc.norm;
+      ep.b_inv = bc.inv_scale;
+      ep.out = w.slab;
+      ep.ldo = w.slab_ld;
+      ep.M = rows;
+      ep.mode = DIST_SQ;
+      ep.rowmax_key = nullptr;
+      ep.run_flag = w.blk_flag + (m0 >> 8);
+      GemmOperands ops;
+      if (rows > kBM) {
+        DEMO_TRY(make_gemm2_operands(a, bc, &ops));
+        const Schedule s = make_dense_schedule2(rows, cols);
+        DEMO_TRY(launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream));
+      } else {
+        DEMO_TRY(make_gemm_operands(a, bc, &ops));
+        const Schedule s = make_dense_schedule(rows, cols);
+        DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+      }
+      CountRows cr;
+      cr.row0 = m0;
+      cr.col_gidx = b_gidx + c0;
+      cr.blk_flag = w.blk_flag;
+      DEMO_TRY(launch_count_matrix(w.slab, w.slab_ld, cols, 0, nullptr, thr_ofs, thr_cnt, thr_val, thr_gidx, counts,
+                                   rows, max_cnt, stream, &cr));
+    }
+  }
+  return DEMO_OK;
+}
+
+// counts[] += #{gallery rows [g0, g0 + gn) (sorted order) lexicographically before each threshold}
+int count_features(const EvalWs& w, int Q, int g0, int gn, const int* thr_ofs, const int* thr_cnt,
+                   const float* thr_val, const int* thr_gidx, unsigned* counts, int max_cnt, int chunk_tiles,
+                   cudaStream_t stream) {
+  if (gn <= 0) return DEMO_OK;
+  const PrepView b = sub_rows(w.b, g0, gn);
+  const int* b_gidx = w.b_gidx + g0;
+  const int G = gn;
+  // Rows with more than one window of thresholds: their 256-row query blocks go to the slab path
+  // (when the workspace holds a slab), everything else is counted in the GEMM epilogue.
+  const bool use_slab = max_cnt > kWin && w.slab != nullptr;
+  if (use_slab) DEMO_TRY(launch_block_flags(thr_cnt, Q, kWin, w.blk_flag, stream));
   GemmOperands ops;
-  DEMO_TRY(make_gemm_operands(w.a, w.b, &ops));
+  DEMO_TRY(make_gemm_operands(w.a, b, &ops));
   EpiCount::Params ep;
   ep.a_norm = w.a.norm;
   ep.a_inv = w.a.inv_scale;
-  ep.b_norm = w.b.norm;
-  ep.b_inv = w.b.inv_scale;
-  ep.b_gidx = w.b_gidx;
+  ep.b_norm = b.norm;
+  ep.b_inv = b.inv_scale;
+  ep.b_gidx = b_gidx;
   ep.thr_ofs = thr_ofs;
   ep.thr_cnt = thr_cnt;
   ep.thr_val = thr_val;
@@ -152,12 +239,14 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
     while (chunk_tiles > 1 && static_cast<long long>(m_blocks) * ceil_div(n_tiles, chunk_tiles) < 8ll * workers)
       chunk_tiles >>= 1;
   }
-  const Schedule s = make_chunked_schedule(Q, G, chunk_tiles, w.a.pitch);
+  Schedule s = make_chunked_schedule(Q, G, chunk_tiles, w.a.pitch);
+  if (use_slab) s.m_skip = w.blk_flag;
   GemmOperands ops2;
   Schedule s2 = s;
   if (pair) {
-    DEMO_TRY(make_gemm2_operands(w.a, w.b, &ops2));
+    DEMO_TRY(make_gemm2_operands(w.a, b, &ops2));
     s2 = make_chunked_schedule2(Q, G, chunk_tiles, w.a.pitch);
+    if (use_slab) s2.m_skip = w.blk_flag;
     // Paced schedule (gemm_sm100.cuh, Schedule::pace): a worker starts its i-th unit only when
     // every worker has issued the loads of its unit i - 2.  Free-running workers drift apart by
     // more than an L2 lifetime within milliseconds and then each re-fetches the gallery tiles its
@@ -175,14 +264,14 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
       s2.pace_steps = pace_steps;
     }
   }
-  const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kWin);
+  const int windows = use_slab ? 1 : ceil_div(max_cnt > 0 ? max_cnt : 1, kWin);
   static const bool no_epi = getenv("DEMO_DEBUG_NOEPI") != nullptr;  // timing experiments only
   for (int wdw = 0; wdw < windows; ++wdw) {
     ep.window = no_epi ? -1 : wdw;
     DEMO_CHECK_CUDA(cudaMemsetAsync(w.ties.hdr, 0, (16 + (s2.pace ? static_cast<size_t>(s2.num_units) * s2.pace_steps + 1 : 0)) * sizeof(unsigned), stream));
     if (pair) DEMO_TRY(launch_sqdist_gemm2<EpiCount>(ops2, s2, s2.num_units, ep, stream));
     else DEMO_TRY(launch_sqdist_gemm<EpiCount>(ops, s, s.num_units, ep, stream));
-    resolve_ties_kernel<<<2 * num_sms(), 256, 0, stream>>>(w.ties, w.b_gidx, thr_ofs, thr_cnt, thr_val, thr_gidx,
+    resolve_ties_kernel<<<2 * num_sms(), 256, 0, stream>>>(w.ties, b_gidx, thr_ofs, thr_cnt, thr_val, thr_gidx,
                                                             counts, wdw);
     DEMO_CHECK_CUDA(cudaGetLastError());
     // exact in-place tie pass; every CTA returns at once unless the list overflowed
@@ -197,6 +286,8 @@ int count_features(const EvalWs& w, int Q, int G, const int* thr_ofs, const int*
       printf("[ties] window %d: %u entries (cap %u), overflow %u, units %d\n", wdw, h[0], w.ties.cap, h[1], s.num_units);
     }
   }
+  if (use_slab)
+    DEMO_TRY(count_slabs(w, Q, b, b_gidx, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, stream));
   return DEMO_OK;
 }
 
@@ -240,20 +331,58 @@ int demo_plan_pointers(const void* plan, size_t plan_bytes, int Q, int G, const 
   return DEMO_OK;
 }
 
-size_t demo_eval_workspace_bytes(int Q, int G, int d, int64_t T) {
-  Carver c(nullptr, ~size_t(0));
-  return round_up(carve_eval(c, Q, G, d, T, nullptr), size_t(1024));
+// Device pointer of the plan's info[4] = {T, max same-pid count, band units, #queried gallery rows}
+// for hosts that enqueue the plan without synchronising and read the numbers later.
+int demo_plan_info(const void* plan, size_t plan_bytes, int Q, int G, const int** info) {
+  PlanView p;
+  DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
+  if (info) *info = p.info;
+  return DEMO_OK;
 }
+
+size_t demo_eval_workspace_bytes_ex(int Q, int G, int d, int64_t T, int max_cnt) {
+  Carver c(nullptr, ~size_t(0));
+  return round_up(carve_eval(c, Q, G, d, T, nullptr, max_cnt), size_t(1024));
+}
+
+size_t demo_eval_workspace_bytes(int Q, int G, int d, int64_t T) { return demo_eval_workspace_bytes_ex(Q, G, d, T, 0); }
 
 size_t demo_eval_matrix_workspace_bytes(int Q, int G, int64_t T) { return demo_eval_workspace_bytes(Q, G, 8, T); }
 
-int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg, int flags,
-                      const int* q_cam, const int* g_cam, int g_index_base, const void* plan,
-                      size_t plan_bytes, int64_t T, void* ws, size_t ws_bytes, float* rec_dist,
-                      int* rec_gidx, int* rec_junk, float* qn_out, float* gn_out, void* stream_) {
+// Prepares (normalise, scale, fp16 hi/lo split) the pid-sorted rows [row0, row0 + nrows) of the
+// queries (which = 0) or the gallery (which = 1) into the evaluation workspace.  x [n][ld] only
+// has to be DEVICE-ACCESSIBLE: with pinned (page-locked) host memory the rows are pulled over
+// PCIe by the kernel itself, in sorted order, without an intermediate fp32 copy in HBM -- this is
+// what lets a host-resident gallery be delivered "queried rows first" (demo_eval_plan) in slabs
+// that the count GEMM consumes while the rest is still in flight.
+int demo_eval_prepare(const float* x, int n, int d, int64_t ld, int flags, int which, int row0, int nrows,
+                      const void* plan, size_t plan_bytes, int Q, int G, int64_t T, void* ws, size_t ws_bytes,
+                      float* xn_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DEMO_REQUIRE(q && g && q_cam && g_cam, "eval_records: null pointer");
-  DEMO_REQUIRE(Q > 0 && G > 0 && d > 0 && ldq >= d && ldg >= d, "eval_records: bad shape");
+  DEMO_REQUIRE(x && d > 0 && ld >= d, "eval_prepare: bad input");
+  DEMO_REQUIRE((which == 0 && n == Q) || (which == 1 && n == G), "eval_prepare: row count does not match the plan");
+  DEMO_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= n, "eval_prepare: row range [%d, %d) outside [0, %d)",
+               row0, row0 + nrows, n);
+  PlanView p;
+  EvalWs w;
+  DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
+  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T, &w));
+  if (nrows == 0) return DEMO_OK;
+  const PrepView v = sub_rows(which ? w.b : w.a, row0, nrows);
+  return launch_prep_rows(x, nrows, d, ld, norm_mode_of(flags), (which ? p.g_perm : p.q_perm) + row0, v, xn_out, d,
+                          stream, (flags & DEMO_FLAG_HOST_INPUT) != 0);
+}
+
+// Records of the same-identity pairs from PREPARED operands (queries + the queried gallery rows,
+// which come first in sorted order): global index and junk flag of every pair, then the tcgen05
+// extract GEMM over the pid bands.  g_index (optional, [G]): global gallery index of every local
+// gallery row, used as the tie-break key instead of g_index_base + local row.
+int demo_eval_extract(int Q, int G, int d, const int* q_cam, const int* g_cam, int g_index_base,
+                      const int* g_index, const void* plan, size_t plan_bytes, int64_t T, void* ws,
+                      size_t ws_bytes, float* rec_dist, int* rec_gidx, int* rec_junk, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEMO_REQUIRE(q_cam && g_cam, "eval_extract: null pointer");
+  DEMO_REQUIRE(Q > 0 && G > 0 && d > 0, "eval_extract: bad shape");
   PlanView p;
   EvalWs w;
   DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
@@ -261,11 +390,8 @@ int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64
   if (!rec_dist) rec_dist = w.rec_dist;
   if (!rec_gidx) rec_gidx = w.rec_gidx;
   if (!rec_junk) rec_junk = w.rec_junk;
-  const int nm = norm_mode_of(flags);
-  DEMO_TRY(launch_prep_rows(q, Q, d, ldq, nm, p.q_perm, w.a, qn_out, d, stream));
-  DEMO_TRY(launch_prep_rows(g, G, d, ldg, nm, p.g_perm, w.b, gn_out, d, stream));
-  gidx_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(p.g_perm, G, g_index_base, w.b_gidx);
-  DEMO_TRY(launch_fill_records(p, q_cam, g_cam, g_index_base, rec_gidx, rec_junk, stream));
+  gidx_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(p.g_perm, G, g_index_base, g_index, w.b_gidx);
+  DEMO_TRY(launch_fill_records(p, q_cam, g_cam, g_index_base, g_index, rec_gidx, rec_junk, stream));
   if (T > 0) {
     GemmOperands ops;
     DEMO_TRY(make_gemm_operands(w.a, w.b, &ops));
@@ -286,6 +412,18 @@ int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64
   return DEMO_OK;
 }
 
+int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg, int flags,
+                      const int* q_cam, const int* g_cam, int g_index_base, const void* plan,
+                      size_t plan_bytes, int64_t T, void* ws, size_t ws_bytes, float* rec_dist,
+                      int* rec_gidx, int* rec_junk, float* qn_out, float* gn_out, void* stream_) {
+  DEMO_REQUIRE(q && g && q_cam && g_cam, "eval_records: null pointer");
+  DEMO_REQUIRE(Q > 0 && G > 0 && d > 0 && ldq >= d && ldg >= d, "eval_records: bad shape");
+  DEMO_TRY(demo_eval_prepare(q, Q, d, ldq, flags, 0, 0, Q, plan, plan_bytes, Q, G, T, ws, ws_bytes, qn_out, stream_));
+  DEMO_TRY(demo_eval_prepare(g, G, d, ldg, flags, 1, 0, G, plan, plan_bytes, Q, G, T, ws, ws_bytes, gn_out, stream_));
+  return demo_eval_extract(Q, G, d, q_cam, g_cam, g_index_base, nullptr, plan, plan_bytes, T, ws, ws_bytes, rec_dist,
+                           rec_gidx, rec_junk, stream_);
+}
+
 int demo_build_thresholds(const int* rec_ofs, const float* rec_dist, const int* rec_gidx, const int* rec_junk,
                           int Q, int* thr_cnt, float* thr_val, int* thr_gidx, int* thr_junk, void* stream_) {
   DEMO_REQUIRE(rec_ofs && thr_cnt, "build_thresholds: null pointer");
@@ -293,13 +431,25 @@ int demo_build_thresholds(const int* rec_ofs, const float* rec_dist, const int* 
                                  static_cast<cudaStream_t>(stream_));
 }
 
+// counts[] += #{gallery rows [g_row0, g_row0 + g_nrows) of the SORTED local gallery before each
+// threshold}; the ranges of successive calls must partition [0, G) (any order, any streams that
+// are ordered after the prepare of their rows).  Rows with more than 63 thresholds use the slab
+// path when the workspace was sized with demo_eval_workspace_bytes_ex(.., max_cnt).
+int demo_eval_count_range(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes, const int* thr_ofs,
+                          const int* thr_cnt, const float* thr_val, const int* thr_gidx, unsigned* counts,
+                          int max_cnt, int chunk_tiles, int g_row0, int g_nrows, void* stream_) {
+  EvalWs w;
+  DEMO_REQUIRE(g_row0 >= 0 && g_nrows >= 0 && g_row0 + g_nrows <= G, "eval_count: gallery range outside [0, %d)", G);
+  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T_local, &w, max_cnt));
+  return count_features(w, Q, g_row0, g_nrows, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, chunk_tiles,
+                        static_cast<cudaStream_t>(stream_));
+}
+
 int demo_eval_count(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes, const int* thr_ofs,
                     const int* thr_cnt, const float* thr_val, const int* thr_gidx, unsigned* counts,
                     int max_cnt, int chunk_tiles, void* stream_) {
-  EvalWs w;
-  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T_local, &w));
-  return count_features(w, Q, G, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, chunk_tiles,
-                        static_cast<cudaStream_t>(stream_));
+  return demo_eval_count_range(Q, G, d, T_local, ws, ws_bytes, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt,
+                               chunk_tiles, 0, G, stream_);
 }
 
 int demo_cmc_map_finalize(const int* thr_ofs, const int* thr_cnt, const int* thr_junk, const unsigned* counts,
@@ -324,14 +474,14 @@ int demo_eval_features(const float* q, const float* g, int Q, int G, int d, int6
   PlanView p;
   EvalWs w;
   DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
-  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T, &w));
+  DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T, &w, max_cnt));
   DEMO_TRY(demo_eval_records(q, g, Q, G, d, ldq, ldg, flags, q_cam, g_cam, 0, plan, plan_bytes, T, ws, ws_bytes,
                              nullptr, nullptr, nullptr, qn_out, gn_out, stream_));
   DEMO_TRY(launch_build_thresholds(p.rec_ofs, w.rec_dist, w.rec_gidx, w.rec_junk, Q, w.thr_cnt, w.thr_val,
                                    w.thr_gidx, w.thr_junk, stream));
   DEMO_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, sizeof(unsigned) * (T > 0 ? T : 1), stream));
   if (T > 0)
-    DEMO_TRY(count_features(w, Q, G, p.rec_ofs, w.thr_cnt, w.thr_val, w.thr_gidx, w.counts, max_cnt, 0, stream));
+    DEMO_TRY(count_features(w, Q, 0, G, p.rec_ofs, w.thr_cnt, w.thr_val, w.thr_gidx, w.counts, max_cnt, 0, stream));
   return launch_finalize(p.rec_ofs, w.thr_cnt, w.thr_junk, w.counts, p.q_perm, Q, max_rank,
                          cmc_out ? cmc_out : w.cmc, map_out ? map_out : w.map, num_valid_out ? num_valid_out : w.nvalid,
                          ap_out ? ap_out : w.ap, first_out ? first_out : w.first, w.scratch, stream);
@@ -349,7 +499,7 @@ int demo_eval_matrix(const float* distmat, int Q, int G, int64_t ld, const int* 
   EvalWs w;
   DEMO_TRY(get_plan(plan, plan_bytes, Q, G, &p));
   DEMO_TRY(get_ws(ws, ws_bytes, Q, G, 8, T, &w));
-  DEMO_TRY(launch_fill_records(p, q_cam, g_cam, 0, w.rec_gidx, w.rec_junk, stream));
+  DEMO_TRY(launch_fill_records(p, q_cam, g_cam, 0, nullptr, w.rec_gidx, w.rec_junk, stream));
   DEMO_TRY(launch_gather_records(p, distmat, ld, w.rec_dist, stream));
   DEMO_TRY(launch_build_thresholds(p.rec_ofs, w.rec_dist, w.rec_gidx, w.rec_junk, Q, w.thr_cnt, w.thr_val,
                                    w.thr_gidx, w.thr_junk, stream));

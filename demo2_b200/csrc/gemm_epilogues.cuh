@@ -74,6 +74,7 @@ struct EpiStore {
     int M;
     int mode;
     unsigned* rowmax_key;  // optional: per-row max of the stored values (ordered-uint keys)
+    const unsigned char* run_flag = nullptr;  // optional (device): the launch is a no-op when *run_flag == 0
   };
   const Params& p;
   EpiColumns cols;
@@ -134,7 +135,7 @@ struct EpiStore {
   }
   __device__ void tile_end(const TileInfo&, int) {}
   __device__ void finish() {}
-  __device__ static bool skip(const Params&) { return false; }
+  __device__ static bool skip(const Params& p) { return p.run_flag != nullptr && *p.run_flag == 0; }
 };
 
 // ---------------------------------------------------------------------------------------

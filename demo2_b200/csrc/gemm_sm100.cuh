@@ -61,6 +61,9 @@ struct Schedule {
   unsigned* pace = nullptr;
   int pace_window = 0, pace_tiles = 1, pace_steps = 1;
   const int* list_count = nullptr; // mode 2: device-side unit count
+  // Optional per-256-row-block flags (device): units of a flagged A block are empty for this launch
+  // (the fused rank count leaves query blocks with more thresholds than one window to the slab path).
+  const unsigned char* m_skip = nullptr;
 };
 
 __device__ __forceinline__ int schedule_num_units(const Schedule& s) {
@@ -100,6 +103,7 @@ __device__ __forceinline__ WorkUnit schedule_get(const Schedule& s, int u) {
     w.n0 = e.y;
     w.n_rows = e.z;
   }
+  if (s.m_skip != nullptr && __ldg(s.m_skip + (w.m0 >> 8)) != 0) w.n_rows = 0;
   return w;
 }
 

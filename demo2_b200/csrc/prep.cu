@@ -3,6 +3,8 @@
 // reads 4*d B and writes 4*d B (hi+lo) per row.
 #include "prep.cuh"
 
+#include <cstdlib>
+
 namespace demo {
 
 namespace {
@@ -49,16 +51,13 @@ __device__ __forceinline__ uint2 pack_half4(__half a, __half b, __half c, __half
 }
 
 // Fast path: d % 4 == 0, 16-byte aligned rows, d <= 128 * kNV.  The row lives in registers
-// (kNV float4 per lane): ONE pass over HBM, float4 loads, 8-byte hi / lo stores.
+// (kNV float4 per lane): ONE pass over the input, float4 loads, 8-byte hi / lo stores.
 template <int kNV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-prep_rows_vec_kernel(const float* __restrict__ x, int rows, int d, long long ldx, int norm_mode,
-                     const int* __restrict__ perm, __half* __restrict__ hi, __half* __restrict__ lo,
-                     int pitch, float* __restrict__ norm, float* __restrict__ inv_scale,
-                     float* __restrict__ xn_out, long long ldxn) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (r >= rows) return;
+__device__ __forceinline__ void prep_row_vec(const float* __restrict__ x, int r, int d, long long ldx, int norm_mode,
+                                             const int* __restrict__ perm, __half* __restrict__ hi,
+                                             __half* __restrict__ lo, int pitch, float* __restrict__ norm,
+                                             float* __restrict__ inv_scale, float* __restrict__ xn_out,
+                                             long long ldxn, int lane) {
   const int src = perm ? __ldg(perm + r) : r;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(src) * ldx);
   const int nvec = d >> 2, pvec = pitch >> 2;
@@ -122,6 +121,36 @@ prep_rows_vec_kernel(const float* __restrict__ x, int rows, int d, long long ldx
   }
 }
 
+template <int kNV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+prep_rows_vec_kernel(const float* __restrict__ x, int rows, int d, long long ldx, int norm_mode,
+                     const int* __restrict__ perm, __half* __restrict__ hi, __half* __restrict__ lo,
+                     int pitch, float* __restrict__ norm, float* __restrict__ inv_scale,
+                     float* __restrict__ xn_out, long long ldxn) {
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  prep_row_vec<kNV>(x, r, d, ldx, norm_mode, perm, hi, lo, pitch, norm, inv_scale, xn_out, ldxn, threadIdx.x & 31);
+}
+
+// Streaming variant for rows that live in pinned HOST memory (zero-copy: the loads go over PCIe).
+// A small grid of 64-thread blocks walks the rows with a grid stride; at <= 80 registers per
+// thread two such blocks fit on an SM NEXT TO a resident CTA of the count GEMM (384 threads x 137
+// registers, 205 KB of shared memory), so a slab of the gallery can be pulled in and prepared
+// while the tensor cores rank the previous slab.  PCIe needs ~0.2 MB in flight; the grid keeps
+// (2 warps x 6 KB) x blocks = several MB.
+constexpr int kStreamWarps = 2;
+template <int kNV>
+__global__ void __launch_bounds__(kStreamWarps * 32, 12)
+prep_rows_stream_kernel(const float* __restrict__ x, int rows, int d, long long ldx, int norm_mode,
+                        const int* __restrict__ perm, __half* __restrict__ hi, __half* __restrict__ lo,
+                        int pitch, float* __restrict__ norm, float* __restrict__ inv_scale,
+                        float* __restrict__ xn_out, long long ldxn) {
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * kStreamWarps;
+  for (int r = blockIdx.x * kStreamWarps + (threadIdx.x >> 5); r < rows; r += stride)
+    prep_row_vec<kNV>(x, r, d, ldx, norm_mode, perm, hi, lo, pitch, norm, inv_scale, xn_out, ldxn, lane);
+}
+
 // Generic path (any d, any alignment): two passes over the row, scalar accesses.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 prep_rows_kernel(const float* __restrict__ x, int rows, int d, long long ldx, int norm_mode,
@@ -180,7 +209,7 @@ prep_rows_kernel(const float* __restrict__ x, int rows, int d, long long ldx, in
 
 int launch_prep_rows(const float* x, int rows, int d, long long ldx, int norm_mode,
                      const int* perm, const PrepView& out, float* xn_out, long long ldxn,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, bool host_input) {
   if (rows <= 0) return DEMO_OK;
   DEMO_REQUIRE(x && out.hi && out.lo && out.norm && out.inv_scale, "prep_rows: null pointer");
   DEMO_REQUIRE(d > 0 && out.pitch >= d && out.pitch % 8 == 0, "prep_rows: bad d/pitch (%d, %d)", d,
@@ -191,6 +220,21 @@ int launch_prep_rows(const float* x, int rows, int d, long long ldx, int norm_mo
 #define DEMO_PREP_VEC(NV)                                                                              \
   prep_rows_vec_kernel<NV><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(                                \
       x, rows, d, ldx, norm_mode, perm, out.hi, out.lo, out.pitch, out.norm, out.inv_scale, xn_out, ldxn)
+  if (host_input && vec) {
+    // zero-copy rows: small persistent grid (see prep_rows_stream_kernel)
+    static const int per_sm = getenv("DEMO_STREAM_BLOCKS") ? atoi(getenv("DEMO_STREAM_BLOCKS")) : 2;
+    const int sblocks = min(ceil_div(rows, kStreamWarps), (per_sm > 0 ? per_sm : 2) * num_sms());
+#define DEMO_PREP_STREAM(NV)                                                                           \
+  prep_rows_stream_kernel<NV><<<sblocks, kStreamWarps * 32, 0, stream>>>(                              \
+      x, rows, d, ldx, norm_mode, perm, out.hi, out.lo, out.pitch, out.norm, out.inv_scale, xn_out, ldxn)
+    if (out.pitch <= 512) DEMO_PREP_STREAM(4);
+    else if (out.pitch <= 1024) DEMO_PREP_STREAM(8);
+    else if (out.pitch <= 1536) DEMO_PREP_STREAM(12);
+    else DEMO_PREP_STREAM(16);
+#undef DEMO_PREP_STREAM
+    DEMO_CHECK_CUDA(cudaGetLastError());
+    return DEMO_OK;
+  }
   if (vec && out.pitch <= 512) DEMO_PREP_VEC(4);
   else if (vec && out.pitch <= 1024) DEMO_PREP_VEC(8);
   else if (vec && out.pitch <= 1536) DEMO_PREP_VEC(12);

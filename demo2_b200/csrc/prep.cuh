@@ -52,8 +52,10 @@ enum : int {
 
 // perm (optional): output row r is input row perm[r].  xn_out (optional): normalised fp32 rows
 // written in INPUT order (row perm[r]).
+// host_input: x is pinned host memory read in place over PCIe (small persistent grid that can
+// share the SMs with a resident GEMM CTA).
 int launch_prep_rows(const float* x, int rows, int d, long long ldx, int norm_mode,
                      const int* perm, const PrepView& out, float* xn_out, long long ldxn,
-                     cudaStream_t stream);
+                     cudaStream_t stream, bool host_input = false);
 
 }  // namespace demo

@@ -27,7 +27,8 @@ int plan_band_cap(int Q, int G) {
 static size_t cub_tmp_bytes_for(int Q, int G) {
   size_t a = 0, b = 0, c = 0;
   int* np = nullptr;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, np, np, np, np, G > 0 ? G : 1);
+  unsigned long long* kp = nullptr;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, kp, kp, np, np, G > 0 ? G : 1);
   cub::DeviceRadixSort::SortPairs(nullptr, b, np, np, np, np, Q > 0 ? Q : 1);
   cub::DeviceScan::ExclusiveSum(nullptr, c, np, np, Q + 1);
   size_t m = a > b ? a : b;
@@ -51,6 +52,8 @@ size_t plan_carve(Carver& c, int Q, int G, PlanView* v) {
   p.info = c.take<int>(4);
   p.iota = c.take<int>(q1 > g1 ? q1 : g1);
   p.cnt = c.take<int>(q1 + 1);
+  p.gkey = c.take<unsigned long long>(g1);
+  p.gkey_sorted = c.take<unsigned long long>(g1);
   p.cub_tmp_bytes = cub_tmp_bytes_for(Q, G);
   p.cub_tmp = c.take<char>(p.cub_tmp_bytes);
   if (v) *v = p;
@@ -64,15 +67,47 @@ __global__ void iota_kernel(int* a, int n) {
   if (i < n) a[i] = i;
 }
 
-// per sorted query: [lower_bound, upper_bound) of its pid in the sorted gallery pids
+// Gallery sort key: rows whose pid is asked for by some query come first ("queried" rows: every
+// record / threshold lives there, so a streamed gallery can deliver them first and the count
+// GEMM can start while the rest is still on its way), then by pid (signed order).
+constexpr unsigned long long kNotQueried = 1ull << 32;
+__global__ void gallery_key_kernel(const int* __restrict__ g_pid, int G, const int* __restrict__ q_pid_sorted, int Q,
+                                   unsigned long long* __restrict__ key) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const int pid = g_pid[i];
+  int lo = 0, hi = Q;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (q_pid_sorted[mid] < pid) lo = mid + 1; else hi = mid;
+  }
+  const bool queried = lo < Q && q_pid_sorted[lo] == pid;
+  key[i] = (queried ? 0ull : kNotQueried) | static_cast<unsigned long long>(static_cast<unsigned>(pid) ^ 0x80000000u);
+}
+
+// sorted keys -> sorted pids; the one thread that sees the class boundary writes P = #queried rows
+__global__ void gallery_unkey_kernel(const unsigned long long* __restrict__ key_sorted, int G,
+                                     int* __restrict__ g_pid_sorted, int* __restrict__ n_queried) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const unsigned long long k = key_sorted[i];
+  g_pid_sorted[i] = static_cast<int>(static_cast<unsigned>(k) ^ 0x80000000u);
+  const bool mine = k < kNotQueried;
+  if (i == 0 && !mine) *n_queried = 0;
+  if (mine && (i + 1 == G || key_sorted[i + 1] >= kNotQueried)) *n_queried = i + 1;
+}
+
+// per sorted query: [lower_bound, upper_bound) of its pid in the queried part of the sorted gallery
 __global__ void ranges_kernel(const int* __restrict__ q_pid_sorted, const int* __restrict__ g_pid_sorted,
-                              int Q, int G, int* __restrict__ g_lo, int* __restrict__ cnt) {
+                              int Q, const int* __restrict__ n_queried, int* __restrict__ g_lo,
+                              int* __restrict__ cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > Q) return;
   if (i == Q) {
     cnt[Q] = 0;
     return;
   }
+  const int G = *n_queried;
   const int pid = q_pid_sorted[i];
   int lo = 0, hi = G;
   while (lo < hi) {
@@ -92,7 +127,8 @@ __global__ void ranges_kernel(const int* __restrict__ q_pid_sorted, const int* _
 // one block: band work list for the extract GEMM + summary numbers
 __global__ void __launch_bounds__(1024)
 band_list_kernel(const int* __restrict__ g_lo, const int* __restrict__ cnt, const int* __restrict__ rec_ofs,
-                 int Q, int4* __restrict__ list, int cap, int* __restrict__ band_count, int* __restrict__ info) {
+                 int Q, int4* __restrict__ list, int cap, int* __restrict__ band_count, int* __restrict__ info,
+                 const int* __restrict__ n_queried) {
   __shared__ int s_scan[1024];
   __shared__ int s_max[1024];
   const int t = threadIdx.x;
@@ -135,7 +171,7 @@ band_list_kernel(const int* __restrict__ g_lo, const int* __restrict__ cnt, cons
     info[0] = rec_ofs[Q];
     info[1] = s_max[1023];
     info[2] = total;
-    info[3] = 0;
+    info[3] = *n_queried;
   }
 }
 
@@ -147,16 +183,21 @@ int run_plan(const int* q_pid, const int* g_pid, const PlanView& p, cudaStream_t
   size_t tmp = p.cub_tmp_bytes;
   const int n = Q > G ? Q : G;
   iota_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(p.iota, n);
-  DEMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(p.cub_tmp, tmp, g_pid, p.g_pid_sorted, p.iota, p.g_perm, G,
-                                                  0, 32, stream));
-  tmp = p.cub_tmp_bytes;
   DEMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(p.cub_tmp, tmp, q_pid, p.q_pid_sorted, p.iota, p.q_perm, Q,
                                                   0, 32, stream));
-  ranges_kernel<<<ceil_div(Q + 1, 256), 256, 0, stream>>>(p.q_pid_sorted, p.g_pid_sorted, Q, G, p.g_lo, p.cnt);
+  // gallery: stable sort by (not queried, pid); p.band_count[1] holds P = #queried rows
+  int* n_queried = p.band_count + 1;
+  gallery_key_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(g_pid, G, p.q_pid_sorted, Q, p.gkey);
+  tmp = p.cub_tmp_bytes;
+  DEMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(p.cub_tmp, tmp, p.gkey, p.gkey_sorted, p.iota, p.g_perm, G,
+                                                  0, 33, stream));
+  gallery_unkey_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(p.gkey_sorted, G, p.g_pid_sorted, n_queried);
+  ranges_kernel<<<ceil_div(Q + 1, 256), 256, 0, stream>>>(p.q_pid_sorted, p.g_pid_sorted, Q, n_queried, p.g_lo,
+                                                          p.cnt);
   tmp = p.cub_tmp_bytes;
   DEMO_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(p.cub_tmp, tmp, p.cnt, p.rec_ofs, Q + 1, stream));
   band_list_kernel<<<1, 1024, 0, stream>>>(p.g_lo, p.cnt, p.rec_ofs, Q, p.band_list, p.band_cap, p.band_count,
-                                           p.info);
+                                           p.info, n_queried);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }
@@ -169,7 +210,8 @@ namespace {
 __global__ void fill_records_kernel(const int* __restrict__ rec_ofs, const int* __restrict__ g_lo,
                                     const int* __restrict__ q_perm, const int* __restrict__ g_perm,
                                     const int* __restrict__ q_cam, const int* __restrict__ g_cam, int Q,
-                                    int g_index_base, int* __restrict__ rec_gidx, int* __restrict__ rec_junk) {
+                                    int g_index_base, const int* __restrict__ g_index,
+                                    int* __restrict__ rec_gidx, int* __restrict__ rec_junk) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= Q) return;
@@ -177,7 +219,7 @@ __global__ void fill_records_kernel(const int* __restrict__ rec_ofs, const int* 
   const int cam = q_cam[q_perm[i]];
   for (int s = lane; s < n; s += 32) {
     const int orig = g_perm[lo + s];
-    rec_gidx[s0 + s] = g_index_base + orig;
+    rec_gidx[s0 + s] = g_index ? g_index[orig] : g_index_base + orig;
     rec_junk[s0 + s] = g_cam[orig] == cam ? 1 : 0;
   }
 }
@@ -254,9 +296,10 @@ build_thresholds_kernel(const int* __restrict__ rec_ofs, const float* __restrict
 }  // namespace
 
 int launch_fill_records(const PlanView& p, const int* q_cam, const int* g_cam, int g_index_base,
-                        int* rec_gidx, int* rec_junk, cudaStream_t stream) {
+                        const int* g_index, int* rec_gidx, int* rec_junk, cudaStream_t stream) {
   fill_records_kernel<<<ceil_div(p.Q * 32, 256), 256, 0, stream>>>(p.rec_ofs, p.g_lo, p.q_perm, p.g_perm, q_cam,
-                                                                   g_cam, p.Q, g_index_base, rec_gidx, rec_junk);
+                                                                   g_cam, p.Q, g_index_base, g_index, rec_gidx,
+                                                                   rec_junk);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }
@@ -293,13 +336,15 @@ __global__ void __launch_bounds__(kCmThreads)
 count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
                     const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
                     const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
-                    const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int window, int skip_small) {
+                    const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int window, int skip_small,
+                    CountRows rows) {
   __shared__ float s_thr[kCmWin];
   __shared__ int s_tg[kCmWin];
   __shared__ unsigned s_hist[kCmWin + 8];
   __shared__ unsigned s_warp[kCmThreads / 32];
-  const int i = blockIdx.x;
+  const int i = rows.row0 + blockIdx.x;   // sorted query
   const int t = threadIdx.x;
+  if (rows.blk_flag && rows.blk_flag[i >> 8] == 0) return;   // block handled by the fused GEMM epilogue
   const int tbase = thr_ofs[i] + window * kCmWin;
   const int nthr = max(0, min(kCmWin, thr_cnt[i] - window * kCmWin));
   if (nthr == 0) return;
@@ -312,7 +357,7 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
   for (int k = t; k < kCmWin + 8; k += kCmThreads) s_hist[k] = 0u;
   __syncthreads();
   const float tmax = s_thr[nthr - 1];
-  const float* row = distmat + static_cast<long long>(q_perm[i]) * ld;
+  const float* row = distmat + static_cast<long long>(q_perm ? q_perm[i] : static_cast<int>(blockIdx.x)) * ld;
   for (int g0 = 0; g0 < G; g0 += kCmThreads * 4) {
     float v[4];
 #pragma unroll
@@ -331,7 +376,8 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
       }
       int pos = lo;
       if (pos > 0 && s_thr[pos - 1] == d) {
-        const int g = g_index_base + g0 + u * kCmThreads + t;
+        const int gc = g0 + u * kCmThreads + t;
+        const int g = rows.col_gidx ? __ldg(rows.col_gidx + gc) : g_index_base + gc;
         while (pos > 0 && s_thr[pos - 1] == d && s_tg[pos - 1] > g) --pos;
       }
       atomicAdd(&s_hist[pos], 1u);
@@ -378,12 +424,13 @@ __global__ void __launch_bounds__(kCfThreads)
 count_matrix63_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
                       const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
                       const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
-                      const int* __restrict__ thr_gidx, unsigned* __restrict__ counts) {
+                      const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, CountRows rows) {
   extern __shared__ unsigned short s_hist[];    // [64][kCfThreads] u16, column = thread (G <= 2^24 per launch)
   __shared__ float s_tab[68];
   __shared__ int s_tg[64];
   __shared__ unsigned s_tot[64];
-  const int i = blockIdx.x, t = threadIdx.x;
+  const int i = rows.row0 + blockIdx.x, t = threadIdx.x;   // i: sorted query
+  if (rows.blk_flag && rows.blk_flag[i >> 8] == 0) return;   // block handled by the fused GEMM epilogue
   const int nthr = thr_cnt[i];
   if (nthr <= 0 || nthr > kCfWin) return;       // larger rows: count_matrix_kernel
   const int tbase = thr_ofs[i];
@@ -402,7 +449,7 @@ count_matrix63_kernel(const float* __restrict__ distmat, long long ld, int G, in
   const float t7 = s_tab[8], t23 = s_tab[24], t39 = s_tab[41], t55 = s_tab[57];
   const uint32_t tab0 = smem_u32(s_tab) + 4;    // address of slot 0
   const uint32_t hist0 = smem_u32(s_hist) + 2 * t;
-  const float* row = distmat + static_cast<long long>(q_perm[i]) * ld;
+  const float* row = distmat + static_cast<long long>(q_perm ? q_perm[i] : static_cast<int>(blockIdx.x)) * ld;
 
   // byte address of slot b = #{thresholds <= d}
   auto search = [&](float d) -> uint32_t {
@@ -428,7 +475,7 @@ count_matrix63_kernel(const float* __restrict__ distmat, long long ld, int G, in
     float below;
     asm("ld.shared.f32 %0, [%1+-4];" : "=f"(below) : "r"(a));
     if (below == d) {                            // bit-equal to a threshold: (distance, index) order
-      const int gi = g_index_base + g;
+      const int gi = rows.col_gidx ? __ldg(rows.col_gidx + g) : g_index_base + g;
       while (b > 0 && s_tab[b <= 32 ? b : b + 1] == d && s_tg[b - 1] > gi) --b;
     }
     const uint32_t h = hist0 + static_cast<uint32_t>(b) * (kCfThreads * 2);
@@ -501,9 +548,11 @@ count_matrix63_kernel(const float* __restrict__ distmat, long long ld, int G, in
 
 int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_base, const int* q_perm,
                         const int* thr_ofs, const int* thr_cnt, const float* thr_val, const int* thr_gidx,
-                        unsigned* counts, int Q, int max_cnt, cudaStream_t stream) {
+                        unsigned* counts, int Q, int max_cnt, cudaStream_t stream, const CountRows* rows_) {
   if (Q <= 0 || G <= 0) return DEMO_OK;
   static_assert(kCmWin == kCmThreads * 8, "scan layout");
+  CountRows rows;
+  if (rows_) rows = *rows_;
   // rows with <= 63 finite thresholds: private-histogram kernel; the others: generic windows
   constexpr int smem = 64 * kCfThreads * 2;
   static PerDeviceInt configured;
@@ -511,15 +560,33 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
   const bool fast = G < (1 << 24) - 512;   // u16 private counters: at most G / 256 (+ head / tail) increments per thread
   if (fast) {
     count_matrix63_kernel<<<Q, kCfThreads, smem, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
-                                                          thr_val, thr_gidx, counts);
+                                                          thr_val, thr_gidx, counts, rows);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kCmWin);
   for (int w = 0; w < windows; ++w) {
     count_matrix_kernel<<<Q, kCmThreads, 0, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
-                                                      thr_val, thr_gidx, counts, w, fast ? 1 : 0);
+                                                      thr_val, thr_gidx, counts, w, fast ? 1 : 0, rows);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
+  return DEMO_OK;
+}
+
+namespace {
+__global__ void block_flags_kernel(const int* __restrict__ thr_cnt, int Q, int win, unsigned char* __restrict__ flag) {
+  const int b = blockIdx.x;
+  int any = 0;
+  for (int i = b * 256 + threadIdx.x; i < min(Q, (b + 1) * 256); i += blockDim.x) any |= thr_cnt[i] > win ? 1 : 0;
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flag[b] = any ? 1 : 0;
+}
+}  // namespace
+
+// flag[b] = 1 when a row of the 256-row query block b has more than `win` thresholds
+int launch_block_flags(const int* thr_cnt, int Q, int win, unsigned char* flag, cudaStream_t stream) {
+  if (Q <= 0) return DEMO_OK;
+  block_flags_kernel<<<ceil_div(Q, 256), 128, 0, stream>>>(thr_cnt, Q, win, flag);
+  DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }
 

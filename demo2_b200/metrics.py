@@ -138,9 +138,14 @@ def cosine_similarity(qf, gf):
 # ------------------------------------------------------------------------------
 class RankPlan:
     """Label-only part of an evaluation (device resident, reusable across evaluations with the
-    same ids): pid-sorted permutations, the record CSR and the extract work list."""
+    same ids): pid-sorted permutations (gallery rows whose pid some query asks for first), the
+    record CSR and the extract work list.
 
-    def __init__(self, q_pids, g_pids, q_camids, g_camids):
+    ``defer=True`` only ENQUEUES the plan: ``info`` (device int32[4] = T, max same-pid count, band
+    units, #queried gallery rows) can then be read together with other data in one host round
+    trip and handed to ``finish``."""
+
+    def __init__(self, q_pids, g_pids, q_camids, g_camids, defer: bool = False):
         lib = _lib.require_device()
         self.q_pid, self.g_pid = _labels(q_pids), _labels(g_pids)
         self.q_cam, self.g_cam = _labels(q_camids), _labels(g_camids)
@@ -149,12 +154,11 @@ class RankPlan:
             raise ValueError("pid / camid length mismatch")
         self.nbytes = lib.demo_plan_bytes(self.Q, self.G)
         self.buf = _ws(self.nbytes)
-        info = (C.c_int64 * 4)()
         check(lib.demo_eval_plan(ptr(self.q_pid), ptr(self.g_pid), self.Q, self.G, ptr(self.buf), self.nbytes,
-                                 info, stream_ptr()))
-        self.T, self.max_cnt, self.band_units = int(info[0]), int(info[1]), int(info[2])
-        ptrs = [C.c_void_p() for _ in range(4)]
-        check(lib.demo_plan_pointers(ptr(self.buf), self.nbytes, self.Q, self.G, *[C.byref(p) for p in ptrs]))
+                                 None, stream_ptr()))
+        ptrs = [C.c_void_p() for _ in range(5)]
+        check(lib.demo_plan_pointers(ptr(self.buf), self.nbytes, self.Q, self.G, *[C.byref(p) for p in ptrs[:4]]))
+        check(lib.demo_plan_info(ptr(self.buf), self.nbytes, self.Q, self.G, C.byref(ptrs[4])))
         base = self.buf.data_ptr()
 
         def view(p, n):
@@ -165,6 +169,14 @@ class RankPlan:
         self.g_perm = view(ptrs[1], self.G)
         self.rec_ofs = view(ptrs[2], self.Q + 1)
         self.g_lo = view(ptrs[3], self.Q)
+        self.info = view(ptrs[4], 4)
+        self.T = self.max_cnt = self.band_units = self.n_queried = None
+        if not defer:
+            self.finish(self.info.cpu())
+
+    def finish(self, info_host):
+        self.T, self.max_cnt, self.band_units, self.n_queried = (int(v) for v in info_host[:4])
+        return self
 
 
 @dataclass
@@ -176,15 +188,53 @@ class EvalResult:
     first: torch.Tensor      # int32 [Q] on device, rank of first correct match, 0 = skipped
     qn: torch.Tensor | None = None
     gn: torch.Tensor | None = None
+    detail: dict | None = None  # device views behind positive_ranks(): thr_ofs, thr_cnt, thr_gidx, thr_junk, counts, q_perm
+
+    def positive_ranks(self):
+        """Per valid positive, in canonical order (query ascending, gallery index ascending):
+        ``(pos_ofs int64[Q+1], gidx int64[T'], r int64[T'], c int64[T'])`` with r_p = 1 + #{valid
+        gallery items before p} and c_p = 1 + #{positives before p}.  Host
+        arrays; this is the index-level result the rank-count kernels produce (tests compare it
+        with the reference's argsort positions)."""
+        return positive_ranks_from_detail(self.detail)
+
+
+def positive_ranks_from_detail(detail):
+    if detail is None:
+        raise ValueError("this result carries no per-positive detail")
+    ofs = detail["thr_ofs"].cpu().numpy().astype(np.int64)
+    cnt = detail["thr_cnt"].cpu().numpy().astype(np.int64)
+    q_perm = detail["q_perm"].cpu().numpy().astype(np.int64)
+    gidx = detail["thr_gidx"].cpu().numpy().astype(np.int64)
+    junk = detail["thr_junk"].cpu().numpy().astype(np.int64)
+    counts = detail["counts"].cpu().numpy().astype(np.int64)
+    Q = len(cnt)
+    per_q = np.zeros(Q, np.int64)
+    per_q[q_perm] = cnt
+    pos_ofs = np.concatenate([[0], np.cumsum(per_q)])
+    T = int(pos_ofs[-1])
+    out_g, out_r, out_c = np.zeros(T, np.int64), np.zeros(T, np.int64), np.zeros(T, np.int64)
+    for i in range(Q):                     # i = position in pid-sorted query order
+        n = int(cnt[i])
+        if n == 0:
+            continue
+        s0, q = int(ofs[i]), int(q_perm[i])
+        g = gidx[s0:s0 + n]
+        r = 1 + counts[s0:s0 + n] - junk[s0:s0 + n]
+        order = np.argsort(g, kind="stable")
+        d0 = int(pos_ofs[q])
+        out_g[d0:d0 + n], out_r[d0:d0 + n], out_c[d0:d0 + n] = g[order], r[order], (np.arange(n) + 1)[order]
+    return pos_ofs, out_g, out_r, out_c
 
 
 class _EvalWorkspace:
     """Caller-owned workspace + typed views of its result slots."""
 
-    def __init__(self, Q, G, d, T, matrix: bool):
+    def __init__(self, Q, G, d, T, matrix: bool, max_cnt: int = 0):
         lib = _lib.load()
         self.Q, self.G, self.d, self.T = Q, G, (8 if matrix else d), T
-        self.nbytes = lib.demo_eval_workspace_bytes(Q, G, self.d, T)
+        # max_cnt > 63: room for the distance slab of the query blocks with long threshold lists
+        self.nbytes = lib.demo_eval_workspace_bytes_ex(Q, G, self.d, T, 0 if matrix else int(max_cnt))
         self.buf = _ws(self.nbytes)
         ptrs = [C.c_void_p() for _ in range(13)]
         check(lib.demo_eval_ws_pointers(ptr(self.buf), self.nbytes, Q, G, self.d, T, *[C.byref(p) for p in ptrs]))
@@ -196,6 +246,12 @@ class _EvalWorkspace:
     def view(self, name, dtype, count):
         o = self.off[name]
         return self.buf[o:o + count * torch.empty((), dtype=dtype).element_size()].view(dtype)
+
+    def detail(self, plan):
+        n = max(self.T, 1)
+        return {"thr_ofs": plan.rec_ofs, "thr_cnt": self.view("thr_cnt", torch.int32, self.Q),
+                "thr_gidx": self.view("thr_gidx", torch.int32, n), "thr_junk": self.view("thr_junk", torch.int32, n),
+                "counts": self.view("counts", torch.int32, n), "q_perm": plan.q_perm}
 
     def read_metrics(self, max_rank):
         # cmc[4096] | map | nvalid live at the tail of the workspace: one D2H copy
@@ -228,7 +284,7 @@ def evaluate_features(qf, gf, q_pids=None, g_pids=None, q_camids=None, g_camids=
     if (Q, G) != (plan.Q, plan.G) or g.shape[1] != d:
         raise ValueError("feature / label shapes disagree")
     max_rank = _effective_max_rank(max_rank, G)
-    w = _EvalWorkspace(Q, G, d, plan.T, matrix=False)
+    w = _EvalWorkspace(Q, G, d, plan.T, matrix=False, max_cnt=plan.max_cnt)
     qn = torch.empty((Q, d), dtype=torch.float32, device=q.device) if want_normalized else None
     gn = torch.empty((G, d), dtype=torch.float32, device=q.device) if want_normalized else None
     flags = _lib.FLAG_L2NORM if normalize else 0
@@ -237,7 +293,8 @@ def evaluate_features(qf, gf, q_pids=None, g_pids=None, q_camids=None, g_camids=
                                  ptr(w.buf), w.nbytes, None, None, None, None, None, ptr(qn), ptr(gn),
                                  stream_ptr()))
     cmc, mAP, nvalid = w.read_metrics(max_rank)
-    return EvalResult(cmc, mAP, nvalid, w.view("ap", torch.float64, Q), w.view("first", torch.int32, Q), qn, gn)
+    return EvalResult(cmc, mAP, nvalid, w.view("ap", torch.float64, Q), w.view("first", torch.int32, Q), qn, gn,
+                      detail=w.detail(plan))
 
 
 def evaluate_matrix(distmat, q_pids=None, g_pids=None, q_camids=None, g_camids=None, max_rank: int = 50,
@@ -256,7 +313,8 @@ def evaluate_matrix(distmat, q_pids=None, g_pids=None, q_camids=None, g_camids=N
                                plan.nbytes, plan.T, plan.max_cnt, max_rank, ptr(w.buf), w.nbytes, None, None,
                                None, None, None, stream_ptr()))
     cmc, mAP, nvalid = w.read_metrics(max_rank)
-    return EvalResult(cmc, mAP, nvalid, w.view("ap", torch.float64, Q), w.view("first", torch.int32, Q))
+    return EvalResult(cmc, mAP, nvalid, w.view("ap", torch.float64, Q), w.view("first", torch.int32, Q),
+                      detail=w.detail(plan))
 
 
 def evaluate_auto(qf, gf, q_pids=None, g_pids=None, q_camids=None, g_camids=None, max_rank: int = 50,

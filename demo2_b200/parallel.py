@@ -67,6 +67,106 @@ def merge_records(cnt_all: torch.Tensor, recs_all: torch.Tensor, sizes=None):
     return ofs.to(torch.int32), merged, T, max_cnt
 
 
+# ------------------------------------------------------------------------------------------------
+# collectives
+# ------------------------------------------------------------------------------------------------
+class TorchCollectives:
+    """torch.distributed (NCCL on GPUs, gloo in the CPU tests).  With a gloo group and CUDA tensors
+    (two processes sharing one GPU in the GPU tests) the payload is staged through the host."""
+
+    name = "torch.distributed"
+
+    def __init__(self, world, rank, group=None):
+        import torch.distributed as dist
+        self.world, self.rank, self.group, self.dist = world, rank, group, dist
+        self.stage = dist.get_backend(group) == "gloo"
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        flat = t.contiguous().view(-1)
+        src = flat.cpu() if (self.stage and flat.is_cuda) else flat
+        out = torch.empty(self.world * src.numel(), dtype=src.dtype, device=src.device)
+        self.dist.all_gather_into_tensor(out, src, group=self.group)
+        return out.to(t.device).view((self.world,) + tuple(t.shape))
+
+    def all_reduce_sum(self, t: torch.Tensor):
+        if self.stage and t.is_cuda:
+            h = t.cpu()
+            self.dist.all_reduce(h, op=self.dist.ReduceOp.SUM, group=self.group)
+            t.copy_(h)
+        else:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def check(self):
+        pass
+
+
+class LibCollectives:
+    """The library's own NCCL communicator (C ABI demo_comm_*): both collectives of an evaluation
+    are enqueued on the compute stream right behind the kernels that produce their inputs.  One
+    communicator per process; the 128-byte id travels through the torch.distributed group."""
+
+    name = "libdemo_b200 NCCL communicator"
+    _ready = None   # (world, rank) once initialised
+
+    def __init__(self, world, rank, group=None):
+        import torch.distributed as dist
+        self.world, self.rank = world, rank
+        self.lib = _lib.require_device()
+        if LibCollectives._ready is None:
+            if not self.lib.demo_comm_available():
+                raise _lib.DemoError("libnccl not available: " + self.lib.demo_last_error().decode())
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                check(self.lib.demo_comm_unique_id(C.c_void_p(ident.data_ptr())))
+            dev = torch.device("cuda", torch.cuda.current_device())
+            on_dev = dist.get_backend(group) != "gloo"
+            t = ident.to(dev) if on_dev else ident
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ident = t.cpu().contiguous()
+            check(self.lib.demo_comm_init(rank, world, C.c_void_p(ident.data_ptr())))
+            LibCollectives._ready = (world, rank)
+        elif LibCollectives._ready != (world, rank):
+            raise _lib.DemoError("the library communicator belongs to rank %d of %d" % LibCollectives._ready[::-1])
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        src = t.contiguous()
+        out = torch.empty((self.world,) + tuple(src.shape), dtype=src.dtype, device=src.device)
+        check(self.lib.demo_comm_all_gather(ptr(src), ptr(out), src.numel() * src.element_size(), stream_ptr()))
+        return out
+
+    def all_reduce_sum(self, t: torch.Tensor):
+        assert t.dtype in (torch.int32, torch.uint32) and t.is_contiguous()
+        check(self.lib.demo_comm_all_reduce_sum_u32(ptr(t), t.numel(), stream_ptr()))
+
+    def check(self):
+        check(self.lib.demo_comm_check())
+
+    @staticmethod
+    def destroy():
+        if LibCollectives._ready is not None:
+            check(_lib.load().demo_comm_destroy())
+            LibCollectives._ready = None
+
+
+def make_collectives(world, rank, group=None, prefer_library: bool = True):
+    """In-library NCCL when the group runs on NCCL (one GPU per process), torch.distributed
+    otherwise (gloo: CPU tests, or two test processes sharing one GPU)."""
+    import torch.distributed as dist
+    if prefer_library and torch.cuda.is_available() and dist.get_backend(group) == "nccl":
+        try:
+            return LibCollectives(world, rank, group)
+        except Exception as exc:  # keep evaluating through torch.distributed, but say so
+            import sys
+            print("demo2_b200: library communicator unavailable (%s); using torch.distributed" % exc, file=sys.stderr)
+    return TorchCollectives(world, rank, group)
+
+
+# ------------------------------------------------------------------------------------------------
+# compute stages
+# ------------------------------------------------------------------------------------------------
+NO_PID = -2 ** 31   # pid of the placeholder gallery row of a rank without gallery items
+
+
 class CudaEngine:
     """The compute stages on one GPU (C ABI of libdemo_b200)."""
 
@@ -75,23 +175,36 @@ class CudaEngine:
 
     def plan(self, q_pid, g_pid, q_cam, g_cam):
         from .metrics import RankPlan
-        return RankPlan(q_pid, g_pid, q_cam, g_cam)
+        return RankPlan(q_pid, g_pid, q_cam, g_cam, defer=True)
 
-    def records(self, plan, qf, gf, g_index_base, normalize):
-        from .metrics import _EvalWorkspace, _features
-        q, g = _features(qf), _features(gf)
-        Q, d = q.shape
-        G = g.shape[0]
-        w = _EvalWorkspace(Q, G, d, plan.T, matrix=False)
-        flags = _lib.FLAG_L2NORM if normalize else 0
-        check(self.lib.demo_eval_records(ptr(q), ptr(g), Q, G, d, q.stride(0), g.stride(0), flags,
-                                         ptr(plan.q_cam), ptr(plan.g_cam), int(g_index_base), ptr(plan.buf),
-                                         plan.nbytes, plan.T, ptr(w.buf), w.nbytes, None, None, None, None, None,
-                                         stream_ptr()))
+    def workspace(self, plan, d, max_cnt):
+        from .metrics import _EvalWorkspace
+        return _EvalWorkspace(plan.Q, plan.G, d, plan.T, matrix=False, max_cnt=max_cnt)
+
+    def prepare(self, plan, w, x, which, row0, nrows, normalize, host_input=False):
+        """pid-sorted rows [row0, row0 + nrows) of the queries (which=0) / gallery (which=1); x is a
+        device tensor, or a PINNED host tensor read in place over PCIe (host_input)."""
+        flags = (_lib.FLAG_L2NORM if normalize else 0) | (_lib.FLAG_HOST_INPUT if host_input else 0)
+        check(self.lib.demo_eval_prepare(ptr(x), x.shape[0], x.shape[1], x.stride(0), flags, which, int(row0),
+                                         int(nrows), ptr(plan.buf), plan.nbytes, plan.Q, plan.G, plan.T, ptr(w.buf),
+                                         w.nbytes, None, stream_ptr()))
+
+    def extract(self, plan, w, g_index_base, g_index=None):
+        check(self.lib.demo_eval_extract(plan.Q, plan.G, w.d, ptr(plan.q_cam), ptr(plan.g_cam), int(g_index_base),
+                                         ptr(g_index), ptr(plan.buf), plan.nbytes, plan.T, ptr(w.buf), w.nbytes,
+                                         None, None, None, stream_ptr()))
         n = max(plan.T, 1)
         recs = torch.stack([w.view("rec_dist", torch.float32, n).view(torch.int32),
                             w.view("rec_gidx", torch.int32, n), w.view("rec_junk", torch.int32, n)])
-        return w, recs[:, :plan.T]
+        return recs[:, :plan.T]
+
+    def records(self, plan, qf, gf, g_index_base, normalize, g_index=None, max_cnt=0):
+        from .metrics import _features
+        q, g = _features(qf), _features(gf)
+        w = self.workspace(plan, q.shape[1], max(max_cnt, plan.max_cnt))
+        self.prepare(plan, w, q, 0, 0, plan.Q, normalize)
+        self.prepare(plan, w, g, 1, 0, plan.G, normalize)
+        return w, self.extract(plan, w, g_index_base, g_index)
 
     def thresholds(self, rec_ofs, recs, Q):
         T = recs.shape[1]
@@ -106,9 +219,11 @@ class CudaEngine:
                                              ptr(thr_cnt), ptr(thr_val), ptr(thr_gidx), ptr(thr_junk), stream_ptr()))
         return thr_cnt, thr_val, thr_gidx, thr_junk
 
-    def count(self, w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt):
-        check(self.lib.demo_eval_count(w.Q, w.G, w.d, plan.T, ptr(w.buf), w.nbytes, ptr(thr_ofs), ptr(thr_cnt),
-                                       ptr(thr_val), ptr(thr_gidx), ptr(counts), int(max_cnt), 0, stream_ptr()))
+    def count(self, w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, g_row0=0, g_nrows=None):
+        g_nrows = w.G - g_row0 if g_nrows is None else g_nrows
+        check(self.lib.demo_eval_count_range(w.Q, w.G, w.d, plan.T, ptr(w.buf), w.nbytes, ptr(thr_ofs), ptr(thr_cnt),
+                                             ptr(thr_val), ptr(thr_gidx), ptr(counts), int(max_cnt), 0, int(g_row0),
+                                             int(g_nrows), stream_ptr()))
 
     def finalize(self, thr_ofs, thr_cnt, thr_junk, counts, q_perm, Q, max_rank):
         dev = counts.device
@@ -123,11 +238,12 @@ class CudaEngine:
                                              ptr(scratch), stream_ptr()))
         return cmc, scal, ap, first
 
-    def launches(self, windows):
-        # iota, ranges, band list | 2x prep, gidx, fill records, extract GEMM | thresholds |
-        # (count GEMM, tie resolver, conditional tie-fix GEMM) x windows | per-query AP, reduce
+    def launches(self, count_launches=1, slab_blocks=0):
+        # plan: iota, gallery key / unkey, ranges, band list | 2x prep, gidx, fill records, extract GEMM |
+        # thresholds | per count launch: count GEMM, tie resolver, conditional tie-fix GEMM (+ per
+        # flagged 256-row block: store GEMM + 2 streaming count kernels) | per-query AP, reduce
         # (CUB sort/scan kernels and memsets not counted)
-        return 3 + 5 + 1 + 3 * windows + 2
+        return 5 + 5 + 1 + 3 * count_launches + 3 * slab_blocks + 2
 
     @staticmethod
     def event():
@@ -137,76 +253,230 @@ class CudaEngine:
 
 
 class ShardedEvaluator:
-    def __init__(self, world: int = 1, rank: int = 0, group=None, engine=None):
+    """Gallery-sharded evaluation of one rank.  Per evaluation there is ONE host round trip before
+    the final read of the metrics: the plan's sizes (and, with several ranks, every rank's sizes,
+    all-gathered on the device first) are read together; everything else is enqueued on the
+    stream -- records, the fixed-size record exchange, thresholds, the count GEMM, the all-reduce
+    of the counts and the finalisation."""
+
+    def __init__(self, world: int = 1, rank: int = 0, group=None, engine=None, collectives=None):
         self.world, self.rank, self.group = world, rank, group
         self.engine = engine if engine is not None else CudaEngine()
+        if collectives is None and world > 1:
+            if isinstance(self.engine, CudaEngine):
+                collectives = make_collectives(world, rank, group)
+            else:
+                collectives = TorchCollectives(world, rank, group)
+        self.coll = collectives
 
-    # -- collectives (torch.distributed; NCCL on GPUs, gloo in the CPU tests) --
-    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
-        import torch.distributed as dist
-        flat = t.contiguous().view(-1)
-        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, flat, group=self.group)
-        return out.view((self.world,) + tuple(t.shape))
+    # ---- label-only part: plan, [sizes of every rank], one host read ---------------------------
+    def _plan_and_sizes(self, q_pid, g_pid_local, q_cam, g_cam_local):
+        eng = self.engine
+        n_local = int(len(g_pid_local))
+        if n_local == 0:
+            # a rank without gallery items still takes part in the exchange: placeholder row that
+            # matches no query, no records, no counting
+            dev = g_pid_local.device if isinstance(g_pid_local, torch.Tensor) else None
+            g_pid_local = torch.full((1,), NO_PID, dtype=torch.int32, device=dev)
+            g_cam_local = torch.zeros(1, dtype=torch.int32, device=dev)
+        plan = eng.plan(q_pid, g_pid_local, q_cam, g_cam_local)
+        Q = plan.Q
+        deferred = plan.T is None
+        if deferred:
+            info = plan.info
+        else:
+            info = torch.tensor([plan.T, plan.max_cnt, 0, 0], dtype=torch.int32, device=plan.rec_ofs.device)
+        sizes = None
+        if self.world > 1:
+            cnt_local = (plan.rec_ofs[1:] - plan.rec_ofs[:-1]).to(torch.int32)
+            meta = torch.cat([cnt_local, info.to(torch.int32),
+                              torch.tensor([n_local], dtype=torch.int32, device=cnt_local.device)])
+            gathered = self.coll.all_gather(meta)                                   # [P, Q + 5]
+            cnt_all = gathered[:, :Q]
+            tot_max = cnt_all.sum(0).max().reshape(1).to(torch.int64) if Q else torch.zeros(1, dtype=torch.int64)
+            host = torch.cat([gathered[:, Q:].reshape(-1).to(torch.int64), tot_max.to(gathered.device)]).cpu()
+            per_rank = host[:-1].reshape(self.world, 5)
+            if deferred:
+                plan.finish(per_rank[self.rank, :4])
+            sizes = dict(cnt_all=cnt_all, t_max=int(per_rank[:, 0].max()), T_sum=int(per_rank[:, 0].sum()),
+                         G_total=int(per_rank[:, 4].sum()), max_all=int(host[-1]))
+        elif deferred:
+            plan.finish(info.cpu())
+        return plan, n_local, sizes
 
-    def _all_reduce_sum(self, t: torch.Tensor):
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+    def _exchange(self, plan, recs, sizes):
+        if self.world > 1:
+            padded = torch.zeros((3, max(sizes["t_max"], 1)), dtype=torch.int32, device=recs.device)
+            padded[:, :recs.shape[1]] = recs
+            recs_all = self.coll.all_gather(padded)
+            return merge_records(sizes["cnt_all"], recs_all, sizes=(sizes["T_sum"], sizes["max_all"]))
+        return plan.rec_ofs, recs, plan.T, plan.max_cnt
+
+    def _finish(self, plan, thr, counts, thr_ofs, G_total, max_rank):
+        from .metrics import EvalResult
+        thr_cnt, thr_val, thr_gidx, thr_junk = thr
+        if G_total < max_rank:
+            max_rank = G_total
+        cmc_d, scal_d, ap, first = self.engine.finalize(thr_ofs, thr_cnt, thr_junk, counts, plan.q_perm, plan.Q,
+                                                        max_rank)
+        # one D2H copy for cmc | mAP | num_valid
+        slab = torch.cat([scal_d.view(torch.uint8), cmc_d.view(torch.uint8)]).cpu()
+        mAP = np.float64(slab[:8].view(torch.float64)[0].item())
+        nvalid = int(slab[8:12].view(torch.int32)[0].item())
+        cmc = slab[32:].view(torch.float32).numpy().copy()
+        if self.coll is not None:
+            self.coll.check()
+        return EvalResult(cmc, mAP, nvalid, ap, first,
+                          detail={"thr_ofs": thr_ofs, "thr_cnt": thr_cnt, "thr_gidx": thr_gidx, "thr_junk": thr_junk,
+                                  "counts": counts, "q_perm": plan.q_perm})
 
     def evaluate(self, qf, gf_local, q_pid, g_pid_local, q_cam, g_cam_local, g_index_base: int = 0,
-                 normalize: bool = False, max_rank: int = 50, timers: dict | None = None):
-        from .metrics import EvalResult
+                 normalize: bool = False, max_rank: int = 50, timers: dict | None = None, g_index=None):
+        """Features on the device (or anything metrics._features accepts).  g_index (optional):
+        global gallery index of every local gallery row -- the tie-break key -- instead of
+        g_index_base + local row."""
         eng = self.engine
         ev = getattr(eng, "event", None) if timers is not None else None
         mark = (lambda: ev()) if ev else (lambda: None)
 
         t0 = mark()
-        plan = eng.plan(q_pid, g_pid_local, q_cam, g_cam_local)
+        plan, n_local, sizes = self._plan_and_sizes(q_pid, g_pid_local, q_cam, g_cam_local)
         Q = plan.Q
         t1 = mark()
-        w, recs = eng.records(plan, qf, gf_local, g_index_base, normalize)
-        t2 = mark()
-        G_total = plan.G
-        if self.world > 1:
-            # one all-gather carries the per-query record counts, the shard's record total and its
-            # gallery size; one host read yields every size the following allocations need
-            cnt_local = (plan.rec_ofs[1:] - plan.rec_ofs[:-1]).to(torch.int32)
-            meta = torch.tensor([plan.T, plan.G], dtype=torch.int32, device=cnt_local.device)
-            gathered = self._all_gather(torch.cat([cnt_local, meta]))          # [P, Q + 2]
-            cnt_all = gathered[:, :Q]
-            tot = cnt_all.sum(0)
-            host = torch.cat([gathered[:, Q:].reshape(-1).to(torch.int64), tot.max().reshape(1)]).cpu()
-            sizes, gsz = host[:-1].reshape(-1, 2)[:, 0], host[:-1].reshape(-1, 2)[:, 1]
-            t_max, T_sum, G_total, max_all = int(sizes.max()), int(sizes.sum()), int(gsz.sum()), int(host[-1])
-            padded = torch.zeros((3, max(t_max, 1)), dtype=torch.int32, device=recs.device)
-            padded[:, :plan.T] = recs
-            recs_all = self._all_gather(padded)
-            thr_ofs, merged, T, max_cnt = merge_records(cnt_all, recs_all, sizes=(T_sum, max_all))
+        max_all = sizes["max_all"] if sizes else plan.max_cnt
+        if n_local > 0:
+            kw = {}
+            if g_index is not None:
+                kw["g_index"] = g_index
+            if isinstance(eng, CudaEngine):
+                kw["max_cnt"] = max_all
+            w, recs = eng.records(plan, qf, gf_local, g_index_base, normalize, **kw)
         else:
-            thr_ofs, merged, T, max_cnt = plan.rec_ofs, recs, plan.T, plan.max_cnt
+            w, recs = None, torch.zeros((3, 0), dtype=torch.int32, device=plan.rec_ofs.device)
+        t2 = mark()
+        thr_ofs, merged, T, max_cnt = self._exchange(plan, recs, sizes)
         t3 = mark()
-        thr_cnt, thr_val, thr_gidx, thr_junk = eng.thresholds(thr_ofs, merged, Q)
+        thr = eng.thresholds(thr_ofs, merged, Q)
         counts = torch.zeros(max(T, 1), dtype=torch.int32, device=merged.device)
         t4 = mark()
-        if T > 0:
-            eng.count(w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt)
+        if T > 0 and n_local > 0:
+            eng.count(w, plan, thr_ofs, thr[0], thr[1], thr[2], counts, max_cnt)
         t5 = mark()
         if self.world > 1:
-            self._all_reduce_sum(counts)
+            self.coll.all_reduce_sum(counts)
         t6 = mark()
-        if G_total < max_rank:
-            max_rank = G_total
-        cmc_d, scal_d, ap, first = eng.finalize(thr_ofs, thr_cnt, thr_junk, counts, plan.q_perm, Q, max_rank)
-        cmc = cmc_d.cpu().numpy()
-        scal = scal_d.cpu()
-        mAP = np.float64(scal[0].item())
-        nvalid = int(scal[1:2].view(torch.int32)[0].item())
+        res = self._finish(plan, thr, counts, thr_ofs, sizes["G_total"] if sizes else n_local, max_rank)
         t7 = mark()
         if timers is not None and ev:
             timers.update({"plan": (t0, t1), "records": (t1, t2), "exchange": (t2, t3), "thresholds": (t3, t4),
                            "count": (t4, t5), "allreduce": (t5, t6), "finalize": (t6, t7)})
-            timers["launches"] = eng.launches(max(1, -(-max_cnt // 63)))
-        return EvalResult(cmc, mAP, nvalid, ap, first)
+            timers["launches"] = eng.launches(1, -(-Q // 256) if max_cnt > 63 else 0)
+        return res
+
+    # ---- host-resident inputs: the gallery is pulled in slab by slab while the GEMM ranks --------
+    def evaluate_host(self, q_host, g_host_local, q_pid, g_pid_local, q_cam, g_cam_local, g_index_base: int = 0,
+                      normalize: bool = False, max_rank: int = 50, timers: dict | None = None,
+                      slab_rows: int = 131072, shard_query_upload: bool = True):
+        """One evaluation whose features live in PINNED HOST memory (what R1_mAP_eval.update
+        accumulates when the model runs elsewhere, utils/metrics.py:244).  No fp32 copy of the
+        gallery is made on the device: demo_eval_prepare pulls the rows over PCIe in pid-sorted
+        order.  The rows some query asks for come first (demo_eval_plan) -- once they are in, the
+        records, thresholds and the count GEMM of that slab run while a side stream pulls in the
+        remaining slabs; every slab is counted as soon as it has landed (rank counts are additive
+        over gallery partitions).  With several ranks each rank uploads 1/P of the queries and
+        the rest arrives over NVLink (all-gather)."""
+        eng = self.engine
+        assert isinstance(eng, CudaEngine), "evaluate_host needs the CUDA engine"
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ev = eng.event if timers is not None else None
+        mark = (lambda: ev()) if ev else (lambda: None)
+        pinned = lambda t: isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned() and t.dtype == torch.float32 \
+            and t.dim() == 2 and t.stride(1) == 1 and t.shape[1] % 4 == 0 and t.shape[1] <= 2048
+
+        t0 = mark()
+        plan, n_local, sizes = self._plan_and_sizes(q_pid, g_pid_local, q_cam, g_cam_local)
+        Q = plan.Q
+        max_all = sizes["max_all"] if sizes else plan.max_cnt
+        t1 = mark()
+        main = torch.cuda.current_stream()
+        d = q_host.shape[1]
+        w = eng.workspace(plan, d, max_all) if n_local > 0 else None
+        # -- queries
+        q_dev = None
+        if self.world > 1 and shard_query_upload and isinstance(self.coll, LibCollectives) and not q_host.is_cuda:
+            per = -(-Q // self.world)
+            lo, hi = min(Q, self.rank * per), min(Q, (self.rank + 1) * per)
+            part = torch.zeros((per, d), dtype=torch.float32, device=dev)
+            part[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
+            q_dev = self.coll.all_gather(part).view(self.world * per, d)[:Q]
+        if n_local > 0:
+            if q_dev is not None:
+                eng.prepare(plan, w, q_dev, 0, 0, Q, normalize)
+            elif pinned(q_host):
+                eng.prepare(plan, w, q_host, 0, 0, Q, normalize, host_input=True)
+            else:
+                from .metrics import _features
+                eng.prepare(plan, w, _features(q_host), 0, 0, Q, normalize)
+        # -- gallery slab 0: the queried rows
+        g_src, g_host_in = g_host_local, pinned(g_host_local)
+        if n_local > 0 and not g_host_in:
+            from .metrics import _features
+            g_src = _features(g_host_local)
+        G = plan.G
+        p0 = min(G, -(-max(plan.n_queried, 1) // 256) * 256) if n_local > 0 else 0
+        bounds = [0, p0]
+        while bounds[-1] < G and n_local > 0:
+            bounds.append(min(G, bounds[-1] + slab_rows))
+        up_events = []
+        if n_local > 0:
+            eng.prepare(plan, w, g_src, 1, 0, p0, normalize, host_input=g_host_in)
+            first_in = torch.cuda.Event()
+            first_in.record(main)
+            side = self._side_stream()
+            side.wait_event(first_in)
+            with torch.cuda.stream(side):
+                for a, b in zip(bounds[1:-1], bounds[2:]):
+                    eng.prepare(plan, w, g_src, 1, a, b - a, normalize, host_input=g_host_in)
+                    e = torch.cuda.Event()
+                    e.record(side)
+                    up_events.append(e)
+            recs = eng.extract(plan, w, g_index_base)
+        else:
+            recs = torch.zeros((3, 0), dtype=torch.int32, device=dev)
+        t2 = mark()
+        thr_ofs, merged, T, max_cnt = self._exchange(plan, recs, sizes)
+        t3 = mark()
+        thr = eng.thresholds(thr_ofs, merged, Q)
+        counts = torch.zeros(max(T, 1), dtype=torch.int32, device=dev)
+        t4 = mark()
+        n_count = 0
+        if n_local > 0:
+            for i, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+                if i > 0:
+                    main.wait_event(up_events[i - 1])
+                if T > 0 and b > a:
+                    eng.count(w, plan, thr_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=a, g_nrows=b - a)
+                    n_count += 1
+        t5 = mark()
+        if self.world > 1:
+            self.coll.all_reduce_sum(counts)
+        t6 = mark()
+        res = self._finish(plan, thr, counts, thr_ofs, sizes["G_total"] if sizes else n_local, max_rank)
+        t7 = mark()
+        if timers is not None and ev:
+            timers.update({"plan": (t0, t1), "upload_queried+records": (t1, t2), "exchange": (t2, t3),
+                           "thresholds": (t3, t4), "count(+upload of the other slabs)": (t4, t5),
+                           "allreduce": (t5, t6), "finalize": (t6, t7)})
+            timers["launches"] = eng.launches(max(n_count, 1), (-(-Q // 256) if max_cnt > 63 else 0) * max(n_count, 1)) \
+                + max(len(bounds) - 3, 0)
+            timers["slabs"] = len(bounds) - 1
+            timers["queried_rows"] = plan.n_queried
+        return res
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(priority=0)
+        return self._side
 
 
 def evaluate_gallery_chunks(qf, gf, q_pid, g_pid, q_cam, g_cam, n_chunks: int, normalize: bool = False,
@@ -223,6 +493,8 @@ def evaluate_gallery_chunks(qf, gf, q_pid, g_pid, q_cam, g_cam, n_chunks: int, n
     for c in range(n_chunks):
         lo, hi = shard_range(G, n_chunks, c)
         plan = eng.plan(q_pid, g_pid[lo:hi], q_cam, g_cam[lo:hi])
+        if plan.T is None:
+            plan.finish(plan.info.cpu())
         w, recs = eng.records(plan, qf, gf[lo:hi], lo, normalize)
         plans.append(plan)
         works.append(w)
@@ -392,9 +664,15 @@ class DistributedR1mAP:
     every sample; samples with ``index < num_query`` are queries (the reference's split,
     utils/metrics.py:347-353).  ``compute()`` all-gathers the (few) query features and labels,
     keeps every rank's gallery features where they are -- they become that rank's gallery shard --
-    and runs the gallery-sharded rank-count evaluation.  Ties are broken by rank-major gallery
-    order (the reference's own tie order is unspecified).  Returns (cmc, mAP) identical on all
-    ranks."""
+    and runs the gallery-sharded rank-count evaluation.
+
+    * A sample that shows up more than once (DistributedSampler pads the tail of the index list by
+      repeating its head when len(dataset) % world != 0) is scored once: the copy on the lowest
+      rank wins, first occurrence within a rank.
+    * Ties are broken by the DATASET order of the gallery (index - num_query is the tie-break key),
+      exactly as a single-process evaluation of the concatenated features would.
+    * A rank that ends up without gallery items still takes part in the exchange.
+    Returns (cmc, mAP), identical on all ranks."""
 
     def __init__(self, num_query, world: int = 1, rank: int = 0, group=None, max_rank=50, feat_norm=True,
                  engine=None):
@@ -414,17 +692,21 @@ class DistributedR1mAP:
         self.index.extend(np.asarray(index.cpu() if isinstance(index, torch.Tensor) else index).tolist())
 
     def _gather_var(self, t: torch.Tensor):
-        """all-gather of tensors whose first dimension differs per rank (padded to the maximum)."""
+        """all-gather of tensors whose first dimension differs per rank (padded to the maximum);
+        staged through the host on a gloo group."""
         import torch.distributed as dist
+        dev = t.device
+        if dist.get_backend(self.group) == "gloo" and t.is_cuda:
+            t = t.cpu()
         n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
         sizes = [torch.zeros_like(n) for _ in range(self.world)]
         dist.all_gather(sizes, n, group=self.group)
         sizes = [int(s.item()) for s in sizes]
-        pad = torch.zeros((max(sizes),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad = torch.zeros((max(max(sizes), 1),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         pad[:t.shape[0]] = t
         out = [torch.empty_like(pad) for _ in range(self.world)]
         dist.all_gather(out, pad, group=self.group)
-        return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0), sizes
+        return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0).to(dev), sizes
 
     def compute(self):
         feats = torch.cat(self.feats, dim=0).float()
@@ -432,20 +714,30 @@ class DistributedR1mAP:
         pids = torch.as_tensor(self.pids, dtype=torch.int64, device=dev)
         cams = torch.as_tensor(self.camids, dtype=torch.int64, device=dev)
         idx = torch.as_tensor(self.index, dtype=torch.int64, device=dev)
+        # first occurrence of every dataset index on this rank, in dataset order
+        idx_s, order = torch.sort(idx, stable=True)
+        first = torch.ones_like(idx_s, dtype=torch.bool)
+        first[1:] = idx_s[1:] != idx_s[:-1]
+        sel = order[first]
+        idx, pids, cams, feats = idx[sel], pids[sel], cams[sel], feats[sel]
+        if self.world > 1:
+            # the copy on the lowest rank wins
+            all_idx, sizes = self._gather_var(idx)
+            below = all_idx[:sum(sizes[:self.rank])]
+            mine = ~torch.isin(idx, below) if below.numel() else torch.ones_like(idx, dtype=torch.bool)
+            idx, pids, cams, feats = idx[mine], pids[mine], cams[mine], feats[mine]
         is_q = idx < self.num_query
         qf, q_lab = feats[is_q], torch.stack([idx[is_q], pids[is_q], cams[is_q]], dim=1)
         gf, g_pid, g_cam = feats[~is_q], pids[~is_q], cams[~is_q]
-        g_base = 0
+        g_index = (idx[~is_q] - self.num_query).to(torch.int32)
         if self.world > 1:
             qf, _ = self._gather_var(qf)
             q_lab, _ = self._gather_var(q_lab)
-            _, g_sizes = self._gather_var(torch.zeros((gf.shape[0], 1), dtype=torch.int64, device=dev))
-            g_base = int(sum(g_sizes[:self.rank]))
         order = torch.argsort(q_lab[:, 0])                 # dataset order of the queries on every rank
         qf, q_lab = qf[order], q_lab[order]
         res = self.evaluator.evaluate(qf, gf, q_lab[:, 1].to(torch.int32), g_pid.to(torch.int32),
-                                      q_lab[:, 2].to(torch.int32), g_cam.to(torch.int32), g_index_base=g_base,
-                                      normalize=bool(self.feat_norm), max_rank=self.max_rank)
+                                      q_lab[:, 2].to(torch.int32), g_cam.to(torch.int32), g_index_base=0,
+                                      normalize=bool(self.feat_norm), max_rank=self.max_rank, g_index=g_index)
         assert res.num_valid > 0, "Error: all query identities do not appear in gallery"
         self.last_result = res
         return res.cmc, res.mAP

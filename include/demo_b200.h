@@ -45,7 +45,8 @@ enum {
   DEMO_DIST_COS_DIST = 3, /* (1-qg/(|q||g|))/2        layers/triplet_loss.py:34-48 cosine_dist       */
   DEMO_FLAG_L2NORM = 0x10,       /* F.normalize rows first   utils/metrics.py:345 */
   DEMO_FLAG_TRIPLET_NORM = 0x20, /* x/(|x|+1e-12) first      layers/triplet_loss.py:5-13 */
-  DEMO_FLAG_SIMT = 0x40          /* FFMA cross-check kernel instead of the tcgen05 GEMM */
+  DEMO_FLAG_SIMT = 0x40,         /* FFMA cross-check kernel instead of the tcgen05 GEMM */
+  DEMO_FLAG_HOST_INPUT = 0x80    /* demo_eval_prepare: x is pinned host memory, read in place over PCIe */
 };
 
 DEMO_API const char* demo_last_error(void);
@@ -81,14 +82,42 @@ DEMO_API int demo_sqdist_f32(const float* q, const float* g, int Q, int G, int d
  * demo_eval_features chains them on one GPU; demo_eval_matrix does the same for a materialised
  * distance matrix (one streaming pass, 4 B per pair).                                         */
 DEMO_API size_t demo_plan_bytes(int Q, int G);
-/* info_host (optional, host int64[4]) = {T records, max same-pid count, band units, 0};
- * when given the call synchronises `stream`. */
+/* The gallery is sorted by (pid not asked for by any query, pid): the "queried" rows -- the only
+ * ones records / thresholds come from -- are the first info[3] rows of the sorted order.
+ * info_host (optional, host int64[4]) = {T records, max same-pid count, band units, #queried
+ * gallery rows}; when given the call synchronises `stream`. */
 DEMO_API int demo_eval_plan(const int* q_pid, const int* g_pid, int Q, int G, void* plan, size_t plan_bytes,
                             int64_t* info_host, void* stream);
 DEMO_API int demo_plan_pointers(const void* plan, size_t plan_bytes, int Q, int G, const int** q_perm,
                                 const int** g_perm, const int** rec_ofs, const int** g_lo);
+/* device pointer of info[4] (same numbers as info_host) for hosts that enqueue the plan without
+ * synchronising and read the numbers later, together with other data */
+DEMO_API int demo_plan_info(const void* plan, size_t plan_bytes, int Q, int G, const int** info);
 DEMO_API size_t demo_eval_workspace_bytes(int Q, int G, int d, int64_t T);
+/* max_cnt > 63 (info[1] of the plan / the merged maximum) adds a 256-row distance slab: query
+ * blocks holding a row with more than 63 thresholds are then counted from ONE stored GEMM pass
+ * (4 B per pair of HBM traffic) instead of one full GEMM per 63 thresholds. */
+DEMO_API size_t demo_eval_workspace_bytes_ex(int Q, int G, int d, int64_t T, int max_cnt);
 DEMO_API size_t demo_eval_matrix_workspace_bytes(int Q, int G, int64_t T);
+/* Staged form of demo_eval_records for streamed / pipelined evaluation
+ * (R1_mAP_eval.compute with host-resident features, utils/metrics.py:341-369):
+ *   demo_eval_prepare     normalise + fp16 hi/lo split of the pid-sorted rows [row0, row0+nrows) of
+ *                         the queries (which = 0) or the gallery (which = 1).  x only has to be
+ *                         DEVICE-ACCESSIBLE: pinned host memory is pulled over PCIe by the kernel
+ *                         itself, in sorted order (queried rows first), slab by slab.
+ *   demo_eval_extract     records from the prepared queries + queried gallery rows; g_index
+ *                         (optional, [G]) = global gallery index per local row (tie-break key).
+ *   demo_eval_count_range counts against the sorted gallery rows [g_row0, g_row0+g_nrows).       */
+DEMO_API int demo_eval_prepare(const float* x, int n, int d, int64_t ld, int flags, int which, int row0, int nrows,
+                               const void* plan, size_t plan_bytes, int Q, int G, int64_t T, void* ws,
+                               size_t ws_bytes, float* xn_out, void* stream);
+DEMO_API int demo_eval_extract(int Q, int G, int d, const int* q_cam, const int* g_cam, int g_index_base,
+                               const int* g_index, const void* plan, size_t plan_bytes, int64_t T, void* ws,
+                               size_t ws_bytes, float* rec_dist, int* rec_gidx, int* rec_junk, void* stream);
+DEMO_API int demo_eval_count_range(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes,
+                                   const int* thr_ofs, const int* thr_cnt, const float* thr_val,
+                                   const int* thr_gidx, unsigned* counts, int max_cnt, int chunk_tiles,
+                                   int g_row0, int g_nrows, void* stream);
 DEMO_API int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg,
                                int flags, const int* q_cam, const int* g_cam, int g_index_base,
                                const void* plan, size_t plan_bytes, int64_t T, void* ws, size_t ws_bytes,
@@ -177,6 +206,26 @@ DEMO_API int demo_triplet_hard_bwd(const float* x, int N, int d, int64_t ld, con
 DEMO_API int demo_hard_example_mining(const float* dist_mat, int N, int64_t ld, const int* labels,
                                       float* dist_ap, float* dist_an, int64_t* p_idx, int64_t* n_idx,
                                       int* npos, void* stream);
+
+/* ---- communicator (multi-GPU evaluation) ----------------------------------
+ * The reference evaluates on rank 0 only (engine/processor.py:145-156); here the gallery is
+ * sharded over one process per GPU and the two exchanges of an evaluation -- all-gather of the
+ * same-identity records, all-reduce(sum) of the rank counts -- run on the compute stream through
+ * an NCCL communicator owned by the library (libnccl is resolved with dlopen at init time; the
+ * copy already loaded by PyTorch is preferred).  One communicator per process.
+ *   demo_comm_unique_id   rank 0: 128-byte id, distributed to the other ranks by the host
+ *   demo_comm_init        collective; the current CUDA device is the rank's device
+ *   demo_comm_check       ncclCommGetAsyncError -> error code                                  */
+DEMO_API int demo_comm_available(void);
+DEMO_API int demo_comm_nccl_version(void);
+DEMO_API int demo_comm_unique_id(void* id_out_host);
+DEMO_API int demo_comm_init(int rank, int world, const void* unique_id_host);
+DEMO_API int demo_comm_destroy(void);
+DEMO_API int demo_comm_info(int* rank, int* world);
+DEMO_API int demo_comm_check(void);
+DEMO_API int demo_comm_all_gather(const void* send, void* recv, size_t bytes_per_rank, void* stream);
+DEMO_API int demo_comm_all_reduce_sum_u32(void* buf, size_t count, void* stream);
+DEMO_API int demo_comm_broadcast(void* buf, size_t bytes, int root, void* stream);
 
 #ifdef __cplusplus
 }

@@ -68,3 +68,73 @@ def batch_loss_case(name: str):
         keep = torch.randperm(P * K, generator=g)[:P * K - 5]
         feats, targets = feats[keep].contiguous(), targets[keep].contiguous()
     return feats, targets
+
+
+# ---- gap-masked rank parity (north_star: rank indices exact wherever the reference's distance gap
+# exceeds the tolerance) -------------------------------------------------------------------------
+GAP_RTOL, GAP_ATOL = 1e-5, 4e-6     # 1e-5 relative on the positive's distance + the absolute floor of two distances
+
+
+def canonical_ranks_from_oracle(dist, qp, gp, qc, gc):
+    """(pos_ofs, gidx, r) of oracle.rank_counts re-ordered canonically (per query by gallery index)."""
+    ofs, idx, r, _ = oracle.rank_counts(dist, qp, gp, qc, gc)
+    g2, r2 = idx.copy(), r.copy()
+    for q in range(len(ofs) - 1):
+        s, e = ofs[q], ofs[q + 1]
+        o = np.argsort(idx[s:e], kind="stable")
+        g2[s:e], r2[s:e] = idx[s:e][o], r[s:e][o]
+    return ofs, g2, r2
+
+
+def compare_ranks_outside_near_ties(pos_ofs, ranks, golden, report_name=None):
+    """Compares per-positive ranks (canonical order) with the reference's (tests/golden/posrank_*):
+    EXACT equality for every positive whose reference gap exceeds the tolerance, exact AP / first
+    rank for the queries without any near-tied positive.  Returns a dict of statistics (masked
+    fractions, mismatches inside the mask) for the parity report."""
+    g_ofs, g_rank, gap, gd = golden["pos_ofs"], golden["rank"].astype(np.int64), golden["gap"], golden["dist"]
+    np.testing.assert_array_equal(pos_ofs, g_ofs)
+    clear = gap > GAP_RTOL * np.abs(gd) + GAP_ATOL
+    ranks = np.asarray(ranks, np.int64)
+    bad = np.nonzero(clear & (ranks != g_rank))[0]
+    assert bad.size == 0, "rank differs on %d positives with a clear gap (first: #%d ours %d ref %d gap %.3g)" % (
+        bad.size, bad[0], ranks[bad[0]], g_rank[bad[0]], gap[bad[0]])
+    Q = len(g_ofs) - 1
+    q_clear = np.array([bool(clear[g_ofs[q]:g_ofs[q + 1]].all()) and g_ofs[q + 1] > g_ofs[q] for q in range(Q)])
+    first_clear = np.zeros(Q, bool)      # the reference's best positive has a clear gap
+    ap_diff, first_bad = 0.0, 0
+
+    def ap_of(r):
+        rs = np.sort(r)
+        return float(((np.arange(len(rs)) + 1) / rs).sum() / len(rs))
+
+    for q in range(Q):
+        s, e = g_ofs[q], g_ofs[q + 1]
+        if e == s:
+            continue
+        best = s + int(np.argmin(g_rank[s:e]))
+        first_clear[q] = clear[best]
+        if first_clear[q]:
+            first_bad += int(ranks[s:e].min() != g_rank[s:e].min())
+        if q_clear[q]:
+            ap_diff = max(ap_diff, abs(ap_of(ranks[s:e]) - ap_of(g_rank[s:e])))
+    assert first_bad == 0, "first-match rank differs on %d queries whose best positive has a clear gap" % first_bad
+    assert ap_diff <= 1e-12
+    stats = {"positives": int(len(g_rank)), "masked_positive_frac": float(1.0 - clear.mean()),
+             "mismatch_inside_mask": int(((ranks != g_rank) & ~clear).sum()),
+             "queries_all_clear_frac": float(q_clear.mean()), "queries_first_clear_frac": float(first_clear.mean())}
+    if report_name:
+        write_parity_report(report_name, stats)
+    return stats
+
+
+def write_parity_report(name, stats):
+    """Measured worst cases of the parity tests, appended to gpurun_out/parity_report.jsonl (scratch;
+    the summary is copied into profiles/ by hand)."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"name": name, **stats}) + "\n")
+    except OSError:
+        pass

@@ -37,8 +37,9 @@ class NumpyEngine:
                                rec_ofs=torch.from_numpy(rec_ofs.astype(np.int32)),
                                q_cam=np.asarray(q_cam), g_cam=np.asarray(g_cam))
 
-    def records(self, plan, qf, gf, g_index_base, normalize):
+    def records(self, plan, qf, gf, g_index_base, normalize, g_index=None):
         qf, gf = np.asarray(qf, np.float32), np.asarray(gf, np.float32)
+        gidx = np.asarray(g_index, np.int64) if g_index is not None else g_index_base + np.arange(len(gf))
         if normalize:
             qf, gf = oracle.l2_normalize(qf), oracle.l2_normalize(gf)
         distmat = oracle.euclidean_distance(qf, gf)
@@ -49,9 +50,9 @@ class NumpyEngine:
             n = ofs[i + 1] - ofs[i]
             cols = plan.g_perm[plan.g_lo[i]:plan.g_lo[i] + n]
             recs[0, ofs[i]:ofs[i + 1]] = distmat[q, cols].view(np.int32)
-            recs[1, ofs[i]:ofs[i + 1]] = g_index_base + cols
+            recs[1, ofs[i]:ofs[i + 1]] = gidx[cols]
             recs[2, ofs[i]:ofs[i + 1]] = plan.g_cam[cols] == plan.q_cam[q]
-        return SimpleNamespace(distmat=distmat, base=g_index_base), torch.from_numpy(recs)
+        return SimpleNamespace(distmat=distmat, gidx=gidx), torch.from_numpy(recs)
 
     def thresholds(self, rec_ofs, recs, Q):
         ofs, recs = rec_ofs.numpy(), recs.numpy()
@@ -75,8 +76,7 @@ class NumpyEngine:
     def count(self, w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt):
         ofs, cnt = thr_ofs.numpy(), thr_cnt.numpy()
         tv, tg, out = thr_val.numpy(), thr_gidx.numpy(), counts.numpy()
-        G = w.distmat.shape[1]
-        gidx = w.base + np.arange(G)
+        gidx = w.gidx
         for i in range(plan.Q):
             row = w.distmat[plan.q_perm[i].item()]
             for k in range(cnt[i]):
@@ -281,34 +281,51 @@ def test_sharded_reranking_matches_oracle(world, k1, k2):
 # ---------------------------------------------------------------------------------------------
 # evaluation under DDP: every rank keeps the features it extracted (parallel.DistributedR1mAP)
 # ---------------------------------------------------------------------------------------------
-def _ddp_worker(rank, world, port, feats, pids, cams, num_query, out):
+def _ddp_worker(rank, world, port, feats, pids, cams, num_query, out, mode):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ev = parallel.DistributedR1mAP(num_query, world=world, rank=rank, group=dist.group.WORLD, feat_norm=False,
                                        engine=NumpyEngine())
-        mine = np.arange(rank, len(pids), world)            # DistributedSampler-style interleaving
+        n = len(pids)
+        if mode == "sampler":
+            # the real thing: DistributedSampler(shuffle=False) pads the index list with its head when
+            # len(dataset) % world != 0, so some samples are extracted twice
+            from torch.utils.data import DistributedSampler
+            mine = np.asarray(list(DistributedSampler(range(n), num_replicas=world, rank=rank, shuffle=False)))
+        elif mode == "queries_only_rank":
+            # rank 0 extracted nothing but queries (no gallery shard of its own)
+            mine = np.arange(0, num_query // 2) if rank == 0 else np.arange(num_query // 2, n)
+        else:
+            mine = np.arange(rank, n, world)                 # interleaving without padding
         for s in range(0, len(mine), 16):
             b = mine[s:s + 16]
             ev.update((torch.from_numpy(feats[b]), pids[b], torch.from_numpy(cams[b]), torch.from_numpy(b)))
         cmc, mAP = ev.compute()
-        out[rank] = (cmc, float(mAP))
+        out[rank] = (cmc, float(mAP), ev.last_result.ap.numpy(), ev.last_result.first.numpy())
     finally:
         dist.destroy_process_group()
 
 
-def test_ddp_evaluator_matches_rank0_evaluation():
+@pytest.mark.parametrize("world,mode", [(2, "interleave"), (3, "sampler"), (2, "queries_only_rank")])
+def test_ddp_evaluator_matches_rank0_evaluation(world, mode):
+    """Every rank keeps what it extracted; the result equals the single-process evaluation of the
+    concatenated features EXACTLY (ties follow the dataset order of the gallery), also when the
+    sampler repeated samples (len % world != 0) and when a rank holds no gallery item."""
     qf, gf, qp, gp, qc, gc = _small_case()
     feats = np.concatenate([qf, gf])
     pids, cams = np.concatenate([qp, gp]), np.concatenate([qc, gc])
-    cmc_o, mAP_o = oracle.eval_func(oracle.euclidean_distance(qf, gf), qp, gp, qc, gc)
-    world = 2
+    assert len(pids) % 3 != 0                                # the sampler case really pads
+    dist_full = oracle.euclidean_distance(qf, gf)
+    cmc_o, mAP_o = oracle.eval_func(dist_full, qp, gp, qc, gc)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_ddp_worker, args=(world, _free_port(), feats, pids, cams, len(qp), out), nprocs=world, join=True)
-    for r in range(world):
-        np.testing.assert_allclose(out[r][0], cmc_o, atol=1e-7)
-        # the small case holds exact duplicates: the rank-major tie order may move an AP by one position
-        assert abs(out[r][1] - mAP_o) < 2e-3
-    assert out[0][1] == out[1][1]
+    mp.spawn(_ddp_worker, args=(world, _free_port(), feats, pids, cams, len(qp), out, mode), nprocs=world, join=True)
+    ofs, idx, r, c = oracle.rank_counts(dist_full, qp, gp, qc, gc)
+    first_o = np.array([r[ofs[q]:ofs[q + 1]].min() if ofs[q + 1] > ofs[q] else 0 for q in range(len(qp))])
+    for rk in range(world):
+        np.testing.assert_allclose(out[rk][0], cmc_o, atol=1e-7)
+        assert abs(out[rk][1] - mAP_o) < 1e-12
+        np.testing.assert_array_equal(out[rk][3], first_o)
+    assert all(out[0][1] == out[rk][1] for rk in range(world))
