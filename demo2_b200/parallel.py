@@ -590,6 +590,11 @@ class ShardedReranker:
         """In-place all-gather of equal row slices: rank r owns rows [r*rpr, (r+1)*rpr)."""
         import torch.distributed as dist
         mine = full[self.rank * rpr:(self.rank + 1) * rpr]
+        if dist.get_backend(self.group) == "gloo" and full.is_cuda:   # two test processes sharing one GPU
+            host = torch.empty(full.shape, dtype=full.dtype)
+            dist.all_gather_into_tensor(host, mine.cpu(), group=self.group)
+            full.copy_(host)
+            return
         dist.all_gather_into_tensor(full, mine.clone(), group=self.group)
 
     def re_ranking(self, probFea, galFea, k1: int, k2: int, lambda_value: float, normalize: bool = False,
@@ -642,7 +647,12 @@ class ShardedReranker:
         if self.world > 1 and not emulate_ranks:
             import torch.distributed as dist
             buf = torch.empty((P * qs, G), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(buf, local[self.rank], group=self.group)
+            if dist.get_backend(self.group) == "gloo" and buf.is_cuda:
+                host = torch.empty(buf.shape, dtype=buf.dtype)
+                dist.all_gather_into_tensor(host, local[self.rank].cpu(), group=self.group)
+                buf.copy_(host)
+            else:
+                dist.all_gather_into_tensor(buf, local[self.rank], group=self.group)
             pieces = {r: buf[r * qs:(r + 1) * qs] for r in range(P)}
         else:
             pieces = local

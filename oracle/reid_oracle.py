@@ -72,10 +72,14 @@ def cosine_similarity(qf, gf):
 # --------------------------------------------------------------------------
 # CMC / mAP
 # --------------------------------------------------------------------------
-def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50, sort_kind: str = "stable"):
+def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50, sort_kind: str = "stable",
+              timing: dict | None = None):
     """Market-1501 protocol (utils/metrics.py:110-169) with the stable tie rule.
     Returns (cmc float32[max_rank], mAP float64).  sort_kind=None reproduces the reference's
-    default (unstable) np.argsort -- used only to TIME the reference algorithm in bench.py."""
+    default (unstable) np.argsort -- used only to TIME the reference algorithm in bench.py, which
+    also asks for the phase split (``timing``: seconds spent in the argsort / the per-query loop)."""
+    import time as _time
+    _t0 = _time.perf_counter()
     distmat = np.asarray(distmat)
     q_pids, g_pids = np.asarray(q_pids), np.asarray(g_pids)
     q_camids, g_camids = np.asarray(q_camids), np.asarray(g_camids)
@@ -84,6 +88,7 @@ def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50, s
         max_rank = num_g
         print("Note: number of gallery samples is quite small, got {}".format(num_g))
     order_all = np.argsort(distmat, axis=1, kind=sort_kind)  # :121
+    _t1 = _time.perf_counter()
     cmc_rows, aps = [], []
     for qi in range(num_q):
         order = order_all[qi]
@@ -98,6 +103,9 @@ def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50, s
         cmc_rows.append(first[:max_rank])
         prec = cum / (np.arange(1, cum.shape[0] + 1) * 1.0)  # :156-158
         aps.append((prec * hits).sum() / hits.sum())  # :159-160
+    if timing is not None:
+        timing["argsort_s"] = _t1 - _t0
+        timing["loop_s"] = _time.perf_counter() - _t1
     assert len(aps) > 0, "Error: all query identities do not appear in gallery"  # :163
     cmc = np.asarray(cmc_rows).astype(F32).sum(0) / float(len(aps))  # :165-166
     return cmc, np.mean(aps)  # :167
