@@ -64,6 +64,10 @@ SIGNATURES = {
     "demo_triplet_hard_fwd": (i32, [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "demo_triplet_hard_bwd": (i32, [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "demo_hard_example_mining": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "demo_triplet_loss_workspace_bytes": (sz, []),
+    "demo_triplet_loss_max_batch": (i32, []),
+    "demo_triplet_loss_fwd": (i32, [vp, i32, i32, i32, i64, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "demo_triplet_loss_bwd": (i32, [vp, i32, i32, i32, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "demo_comm_available": (i32, []),
     "demo_comm_nccl_version": (i32, []),
     "demo_comm_unique_id": (i32, [vp]),

@@ -6,13 +6,19 @@
     TripletLoss / MultiModalTripletLoss(margin=None, hard_factor=0.0)
         .__call__(global_feat, labels, normalize_feature=False) -> (loss, dist_ap, dist_an)   (:107-167)
 
-``TripletLoss`` takes the fused path: distance GEMM + hard mining in one tcgen05 kernel
-(the N x N matrix is never written) and a sparse backward (only the 2N selected pairs carry
-gradient).  The free functions keep the reference's signatures for callers that build the
-matrix themselves.  All arithmetic is fp32 (the reference runs the matmul in fp16 under
-autocast on GPU).
+``TripletLoss`` takes a fused path.  Training-size batches (N <= 256, the reference's PK batches
+are 64 or 128) run ONE kernel for the whole forward -- fp32 Gram matrix, sqrt / clamp, hard
+mining, ranking loss and its mean, for all modalities at once (``triplet_loss_multi``) -- and one
+kernel for the backward; there is no host synchronisation (the PK-batch check of the reference's
+``view(N, -1)`` is evaluated on the device and inspected at the next call).  Larger batches use
+the tcgen05 distance GEMM with the mining fused into its epilogue (the N x N matrix is never
+written) and a sparse backward.  The free functions keep the reference's signatures for callers
+that build the matrix themselves.  All arithmetic is fp32 (the reference runs the matmul in fp16
+under autocast on GPU).
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 from torch import nn
@@ -122,6 +128,8 @@ class _FusedHardTriplet(torch.autograd.Function):
         lib = _lib.require_device()
         x = x.contiguous() if x.stride(1) != 1 else x
         N, d = x.shape
+        if N > 3072:   # the backward kernel keeps 16 bytes per anchor in 48 KB of shared memory
+            raise ValueError("fused TripletLoss supports up to 3072 anchors per batch (got %d)" % N)
         lab = _labels_i32(labels, x.device)
         ap = torch.empty(N, dtype=torch.float32, device=x.device)
         an = torch.empty(N, dtype=torch.float32, device=x.device)
@@ -158,13 +166,139 @@ def fused_hard_mining(global_feat, labels, check_pk: bool = True):
     return _FusedHardTriplet.apply(x, labels, check_pk)
 
 
+# ------------------------------------------------------------------------------------------------
+# one-launch path for training-size batches
+# ------------------------------------------------------------------------------------------------
+_SMALL_WS = {}        # device index -> zero-initialised workspace (tickets return to 0 after every launch)
+_PENDING = []         # (pinned status copy, event, description) of launches not inspected yet
+
+
+def _small_limit() -> int:
+    return int(_lib.load().demo_triplet_loss_max_batch())
+
+
+def _small_workspace(dev) -> torch.Tensor:
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _SMALL_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().demo_triplet_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _SMALL_WS[key] = ws
+    return ws
+
+
+def _raise_for_status(bits: int, when: str):
+    if bits & 1:
+        raise RuntimeError("hard_example_mining: anchors have different numbers of positives (the reference's "
+                           "view(N, -1) at layers/triplet_loss.py:79 requires a PK batch)" + when)
+    if bits & 2:
+        raise RuntimeError("hard_example_mining: an anchor has no negative sample in the batch" + when)
+
+
+def check_pending_status(block: bool = False):
+    """Inspects the device-side batch checks of earlier fused launches (unequal numbers of positives,
+    anchors without a negative) without stalling the stream: entries whose copy has completed are
+    read, the others stay queued unless ``block``."""
+    while _PENDING:
+        host, ev = _PENDING[0]
+        if not block and not ev.query():
+            return
+        ev.synchronize()
+        _PENDING.pop(0)
+        _raise_for_status(int(host.max().item()) if host.numel() else 0, " [reported by an earlier TripletLoss call]")
+
+
+class _TripletLossFused(torch.autograd.Function):
+    """(loss[B], dist_ap[B, N], dist_an[B, N]) for B feature matrices sharing the labels: one
+    forward kernel, one backward kernel."""
+
+    @staticmethod
+    def forward(ctx, labels, margin, hard_factor, check, *xs):
+        lib = _lib.require_device()
+        xs = tuple(x if (x.stride(1) == 1 and x.stride(0) == xs[0].stride(0)) else x.contiguous() for x in xs)
+        if any(x.stride(0) != xs[0].stride(0) for x in xs):
+            xs = tuple(x.contiguous() for x in xs)
+        B = len(xs)
+        N, d = xs[0].shape
+        dev = xs[0].device
+        lab = labels.to(dev)
+        if lab.dtype not in (torch.int32, torch.int64):
+            lab = lab.to(torch.int64)
+        lab = lab.contiguous()
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        ap = torch.empty((B, N), dtype=torch.float32, device=dev)
+        an = torch.empty((B, N), dtype=torch.float32, device=dev)
+        p_inds = torch.empty((B, N), dtype=torch.int64, device=dev)
+        n_inds = torch.empty((B, N), dtype=torch.int64, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev) if check else None
+        ws = _small_workspace(dev)
+        ptrs = (C.c_void_p * B)(*[x.data_ptr() for x in xs])
+        m = -1.0 if margin is None else float(margin)
+        _lib.check(lib.demo_triplet_loss_fwd(ptrs, B, N, d, xs[0].stride(0), ptr(lab), 1 if lab.dtype == torch.int64 else 0,
+                                             m, float(hard_factor), ptr(loss), ptr(ap), ptr(an), ptr(p_inds), ptr(n_inds),
+                                             ptr(status), ptr(ws), ws.numel(), stream_ptr()))
+        if check == "now":
+            _raise_for_status(int(status.max().item()), "")
+        elif check:
+            host = torch.empty(B, dtype=torch.int32, pin_memory=True)
+            host.copy_(status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            _PENDING.append((host, ev))
+        ctx.save_for_backward(ap, an, p_inds, n_inds, *xs)
+        ctx.margin, ctx.hard_factor = m, float(hard_factor)
+        ctx.mark_non_differentiable(p_inds, n_inds)
+        return loss, ap, an, p_inds, n_inds
+
+    @staticmethod
+    def backward(ctx, g_loss, g_ap, g_an, _gp, _gn):
+        lib = _lib.require_device()
+        ap, an, p_inds, n_inds, *xs = ctx.saved_tensors
+        B = len(xs)
+        N, d = xs[0].shape
+        dev = xs[0].device
+        g_loss = None if g_loss is None else g_loss.contiguous().float()
+        g_ap = None if g_ap is None else g_ap.contiguous().float()
+        g_an = None if g_an is None else g_an.contiguous().float()
+        grad = torch.empty((B, N, d), dtype=torch.float32, device=dev)
+        ptrs = (C.c_void_p * B)(*[x.data_ptr() for x in xs])
+        _lib.check(lib.demo_triplet_loss_bwd(ptrs, B, N, d, xs[0].stride(0), ctx.margin, ctx.hard_factor, ptr(ap), ptr(an),
+                                             ptr(p_inds), ptr(n_inds), ptr(g_loss), ptr(g_ap), ptr(g_an), ptr(grad), d,
+                                             stream_ptr()))
+        return (None, None, None, None) + tuple(grad[b] for b in range(B))
+
+
+def triplet_loss_multi(feats, labels, margin=None, hard_factor=0.0, check="deferred", return_inds: bool = False):
+    """TripletLoss for several same-shaped feature matrices that share the labels -- the per-modality
+    calls of layers/make_loss.py:47-52 (RGB / NIR / TIR heads of one batch) -- in ONE kernel.
+    Returns (loss [B], dist_ap [B, N], dist_an [B, N]) (+ p_inds, n_inds); row b is exactly what
+    ``TripletLoss(margin, hard_factor)(feats[b], labels)`` returns.  N <= 256.
+
+    ``check``: "deferred" (default) evaluates the reference's implicit batch requirements (equal
+    number of positives per anchor, a negative for every anchor) on the device and raises at the
+    next call, with no synchronisation; "now" synchronises and raises immediately; False skips."""
+    xs = [_as_cuda_f32(x) for x in feats]
+    N = xs[0].shape[0]
+    if N > _small_limit():
+        raise ValueError("triplet_loss_multi handles up to %d anchors per batch (got %d)" % (_small_limit(), N))
+    if any(tuple(x.shape) != tuple(xs[0].shape) for x in xs):
+        raise ValueError("all feature matrices must have the same shape")
+    check_pending_status()
+    loss, ap, an, p_inds, n_inds = _TripletLossFused.apply(labels, margin, hard_factor, check, *xs)
+    if return_inds:
+        return loss, ap, an, p_inds, n_inds
+    return loss, ap, an
+
+
 class TripletLoss(object):
     """
-    Triplet loss using HARDER example mining (layers/triplet_loss.py:107-135), fused
-    distance + mining forward and sparse backward.
+    Triplet loss using HARDER example mining (layers/triplet_loss.py:107-135).  Batches of up to
+    256 anchors: one fused kernel (distance + mining + loss); larger: tcgen05 distance GEMM with
+    the mining in its epilogue.  ``check_pk``: "deferred" (default; no host synchronisation, a
+    malformed batch raises at the next call), True (synchronise and raise immediately, as the
+    reference's view(N, -1) would), False.
     """
 
-    def __init__(self, margin=None, hard_factor=0.0, check_pk=True):
+    def __init__(self, margin=None, hard_factor=0.0, check_pk="deferred"):
         self.margin = margin
         self.hard_factor = hard_factor
         self.check_pk = check_pk
@@ -173,10 +307,23 @@ class TripletLoss(object):
         else:
             self.ranking_loss = nn.SoftMarginLoss()
 
+    def forward_multi(self, feats, labels, normalize_feature=False):
+        """All modalities of one batch in one launch: (loss [B], dist_ap [B, N], dist_an [B, N])."""
+        if normalize_feature:
+            feats = [normalize(f, axis=-1) for f in feats]
+        check = "now" if self.check_pk is True else self.check_pk
+        return triplet_loss_multi(feats, labels, self.margin, self.hard_factor, check)
+
     def __call__(self, global_feat, labels, normalize_feature=False):
         if normalize_feature:
             global_feat = normalize(global_feat, axis=-1)
-        dist_ap, dist_an, _, _ = fused_hard_mining(global_feat, labels, self.check_pk)
+        if global_feat.dim() == 2 and global_feat.shape[0] <= _small_limit():
+            check = "now" if self.check_pk is True else self.check_pk
+            loss, dist_ap, dist_an = triplet_loss_multi([global_feat], labels, self.margin, self.hard_factor, check)
+            return loss[0], dist_ap[0], dist_an[0]
+        dist_ap, dist_an, _, n_inds = fused_hard_mining(global_feat, labels, bool(self.check_pk))
+        if self.check_pk and bool((n_inds < 0).any()):
+            raise RuntimeError("hard_example_mining: an anchor has no negative sample in the batch")
 
         dist_ap = dist_ap * (1.0 + self.hard_factor)
         dist_an = dist_an * (1.0 - self.hard_factor)

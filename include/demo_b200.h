@@ -207,6 +207,31 @@ DEMO_API int demo_hard_example_mining(const float* dist_mat, int N, int64_t ld, 
                                       float* dist_ap, float* dist_an, int64_t* p_idx, int64_t* n_idx,
                                       int* npos, void* stream);
 
+/* Training-size batches (N <= demo_triplet_loss_max_batch() = 256): the WHOLE TripletLoss forward
+ * of layers/triplet_loss.py:121-135 -- euclidean_dist, hard_example_mining, the (1 +- hard_factor)
+ * scaling, SoftMarginLoss (margin < 0 / NaN = the reference's margin=None) or MarginRankingLoss and
+ * its mean -- in ONE launch for B <= 8 feature matrices sharing the labels (the per-modality calls
+ * of layers/make_loss.py:47-52), and the whole backward in another.
+ *   xs      HOST array of B device pointers, each [N][ld] fp32
+ *   labels  device int32 (label_is_i64 = 0) or int64 (1, the reference's LongTensor)
+ *   loss [B]; dist_ap / dist_an [B][N] as the reference returns them (already scaled); p_idx /
+ *   n_idx [B][N] (n_idx = -1: no negative); status [B] (optional): bit 0 = anchors with different
+ *   numbers of positives (the reference's view(N, -1) at :79 raises), bit 1 = anchor without negative
+ *   ws      demo_triplet_loss_workspace_bytes() bytes, zero-initialised ONCE by the caller
+ *   bwd     g_loss [B] (optional), g_ap_ext / g_an_ext [B][N] (optional upstream gradients of the
+ *           returned distances) -> grad [B][N][ldg]                                              */
+DEMO_API size_t demo_triplet_loss_workspace_bytes(void);
+DEMO_API int demo_triplet_loss_max_batch(void);
+DEMO_API int demo_triplet_loss_fwd(const float* const* xs, int B, int N, int d, int64_t ld, const void* labels,
+                                   int label_is_i64, float margin, float hard_factor, float* loss, float* dist_ap,
+                                   float* dist_an, int64_t* p_idx, int64_t* n_idx, int* status, void* ws,
+                                   size_t ws_bytes, void* stream);
+DEMO_API int demo_triplet_loss_bwd(const float* const* xs, int B, int N, int d, int64_t ld, float margin,
+                                   float hard_factor, const float* dist_ap, const float* dist_an,
+                                   const int64_t* p_idx, const int64_t* n_idx, const float* g_loss,
+                                   const float* g_ap_ext, const float* g_an_ext, float* grad, int64_t ldg,
+                                   void* stream);
+
 /* ---- communicator (multi-GPU evaluation) ----------------------------------
  * The reference evaluates on rank 0 only (engine/processor.py:145-156); here the gallery is
  * sharded over one process per GPU and the two exchanges of an evaluation -- all-gather of the

@@ -119,6 +119,67 @@ def test_unequal_positives_raise(T):
     x = torch.randn(6, 16, device="cuda")
     labels = torch.tensor([0, 0, 0, 1, 1, 2], device="cuda")
     with pytest.raises(RuntimeError):
-        T.TripletLoss()(x, labels)
+        T.TripletLoss(check_pk=True)(x, labels)          # synchronous, as the reference's view(N, -1)
+    # default: evaluated on the device, reported without stalling the stream -- at the latest by an explicit check
+    T.TripletLoss()(x, labels)
+    with pytest.raises(RuntimeError):
+        T.check_pending_status(block=True)
+    T.check_pending_status(block=True)                   # the queue is drained
     with pytest.raises(RuntimeError):
         T.hard_example_mining(T.euclidean_dist(x, x), labels)
+    # an anchor without any negative (single identity)
+    with pytest.raises(RuntimeError):
+        T.TripletLoss(check_pk=True)(x, torch.zeros(6, dtype=torch.long, device="cuda"))
+
+
+def test_one_launch_path_all_modalities(T):
+    """triplet_loss_multi: the three per-modality TripletLoss calls of a training step in one kernel
+    == the reference's golden values per modality, forward and backward."""
+    g = load_golden("triplet_pk8x16_d768")
+    xs, labels = synth.make_triplet_batch()
+    xr = [x.cuda().requires_grad_(True) for x in xs]
+    loss, ap, an, pi, ni = T.triplet_loss_multi(xr, labels.cuda(), return_inds=True, check="now")
+    assert loss.shape == (3,) and ap.shape == (3, 128)
+    loss.sum().backward()
+    for m in range(3):
+        np.testing.assert_allclose(loss[m].item(), g["loss%d" % m], rtol=1e-5)
+        np.testing.assert_allclose(ap[m].detach().cpu().numpy(), g["ap%d" % m], rtol=RTOL)
+        np.testing.assert_allclose(an[m].detach().cpu().numpy(), g["an%d" % m], rtol=RTOL)
+        np.testing.assert_array_equal(pi[m].cpu().numpy(), g["pi%d" % m])
+        np.testing.assert_array_equal(ni[m].cpu().numpy(), g["ni%d" % m])
+        np.testing.assert_allclose(xr[m].grad.cpu().numpy(), g["grad%d" % m], rtol=1e-4, atol=1e-7)
+    # margin / hard_factor / normalised features through the class (single modality, one launch)
+    for m, x in enumerate(xs):
+        xm = x.cuda().requires_grad_(True)
+        lossm, apm, anm = T.TripletLoss(margin=0.3, hard_factor=0.1)(xm, labels.cuda(), normalize_feature=True)
+        lossm.backward()
+        np.testing.assert_allclose(lossm.item(), g["lossm%d" % m], rtol=1e-5)
+        np.testing.assert_allclose(apm.detach().cpu().numpy(), g["apm%d" % m], rtol=1e-4)
+        np.testing.assert_allclose(anm.detach().cpu().numpy(), g["anm%d" % m], rtol=1e-4)
+        np.testing.assert_allclose(xm.grad.cpu().numpy(), g["gradm%d" % m], rtol=2e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("P,K,d,margin,hf", [(5, 7, 100, None, 0.0), (8, 32, 512, 0.3, 0.1), (4, 50, 33, None, 0.2),
+                                             (2, 3, 1, 1.0, 0.0), (16, 16, 2048, None, 0.0)])
+def test_one_launch_path_ragged_shapes_vs_torch(T, P, K, d, margin, hf):
+    """Odd batch sizes / feature widths (not multiples of the 8-row blocks, the 4-wide loads or the
+    32-wide k-chunks), up to the 256-anchor limit, both losses: forward and backward against a plain
+    PyTorch fp32 restatement with autograd, plus upstream gradients through the returned distances."""
+    torch.manual_seed(P * 1000 + K)
+    N = P * K
+    labels = torch.arange(P, device="cuda").repeat_interleave(K)[torch.randperm(N, device="cuda")]
+    x = torch.randn(N, d, device="cuda") + 0.5 * torch.randn(P, d, device="cuda")[labels]
+    xa = x.clone().requires_grad_(True)
+    loss, ap, an = T.TripletLoss(margin=margin, hard_factor=hf, check_pk=True)(xa, labels)
+    w = torch.randn(N, device="cuda")
+    (loss + 0.01 * (w * ap).sum() - 0.02 * (w * an).sum()).backward()
+    xb = x.clone().requires_grad_(True)
+    lt, apt, ant = torch_ref_loss(xb, labels, margin=margin, hard_factor=hf)
+    (lt + 0.01 * (w * apt).sum() - 0.02 * (w * ant).sum()).backward()
+    np.testing.assert_allclose(loss.item(), lt.item(), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(ap.detach().cpu().numpy(), apt.detach().cpu().numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(an.detach().cpu().numpy(), ant.detach().cpu().numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(xa.grad.cpu().numpy(), xb.grad.cpu().numpy(), rtol=2e-3, atol=2e-6)
+    # repeated launches reuse the self-resetting workspace
+    loss2, _, _ = T.TripletLoss(margin=margin, hard_factor=hf)(x, labels)
+    assert loss2.item() == loss.item()
