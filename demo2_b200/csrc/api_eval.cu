@@ -31,13 +31,16 @@ struct EvalWs {
   TieList ties;           // exact-tie list of the count GEMM (entries + {count, overflow})
   unsigned* pace;         // per-iteration arrival counters of the paced CTA-pair schedule
   size_t pace_cap;
-  unsigned char* blk_flag;  // [ceil(Q/256)] query blocks with a row of more than kWin thresholds (slab path)
-  float* slab;            // [kSlabRows][slab_ld] distance slab of the flagged query blocks; nullptr = not carved
-  int slab_ld;
+  unsigned char* blk_flag;    // [ceil(Q/256)] query blocks with a row of more than kWin thresholds (slab path)
+  unsigned char* blk_unflag;  // [ceil(Q/256)] the complement (schedule skip list of the slab GEMM)
+  unsigned char* slab_any;    // [ceil(Q/slab_rows)] slabs with a flagged block
+  float* slab;                // [slab_rows][slab_ld] distance slab of the flagged query blocks; nullptr = not carved
+  int slab_ld, slab_rows;
 };
 
-constexpr int kSlabRows = 256;        // one CTA-pair block of queries
-constexpr int kSlabMaxCols = 1 << 20; // gallery columns per slab pass (1 GB of fp32 at most)
+constexpr int kSlabMaxRows = 1024;    // query rows per slab (4 CTA-pair blocks): enough blocks to keep the
+                                      // streaming count kernels at HBM speed
+constexpr int kSlabMaxCols = 1 << 20; // gallery columns per slab pass (4 GB of fp32 at most)
 
 // Capacity of the tie list: every valid positive ties with its own threshold (<= T entries per
 // window) plus coincidental bit-equal distances; beyond it the exact tie-fix pass takes over.
@@ -73,12 +76,16 @@ size_t carve_eval(Carver& c, int Q, int G, int d, long long T, EvalWs* w, int ma
   t.ties.hdr = c.take<unsigned>(16 + t.pace_cap);
   t.pace = t.ties.hdr + 16;
   t.ties.entries = c.take<int4>(t.ties.cap);
-  t.blk_flag = c.take<unsigned char>(ceil_div(static_cast<int>(q1), 256) + 16);
+  const int nb = ceil_div(static_cast<int>(q1), 256);
+  t.blk_flag = c.take<unsigned char>(3 * (nb + 16));
+  t.blk_unflag = t.blk_flag + nb + 16;
+  t.slab_any = t.blk_unflag + nb + 16;
   t.slab = nullptr;
   t.slab_ld = 0;
+  t.slab_rows = 256 * (nb < kSlabMaxRows / 256 ? nb : kSlabMaxRows / 256);
   if (max_cnt > kWin) {
     t.slab_ld = static_cast<int>(round_up(g1 < static_cast<size_t>(kSlabMaxCols) ? g1 : static_cast<size_t>(kSlabMaxCols), size_t(4)));
-    t.slab = c.take<float>(static_cast<size_t>(kSlabRows) * t.slab_ld);
+    t.slab = c.take<float>(static_cast<size_t>(t.slab_rows) * t.slab_ld);
   }
   if (w) *w = t;
   return c.off;
@@ -153,14 +160,15 @@ PrepView sub_rows(const PrepView& v, int row0, int nrows) {
 }
 
 // Slab path for the query blocks flagged in w.blk_flag (a row with more than kWin thresholds):
-// per 256-row block the distances against the gallery range are stored once (EpiStore; the launch
-// is a no-op for unflagged blocks) and counted by the streaming kernels of rank.cu, whatever the
-// number of thresholds -- one GEMM pass plus 4 B per pair of HBM traffic instead of one full GEMM
-// per 63 thresholds.
+// per slab of up to 1024 query rows the distances of the flagged 256-row blocks against the
+// gallery range are stored once (EpiStore; unflagged blocks are skipped, a slab without flagged
+// block is a no-op) and counted by the streaming kernels of rank.cu, whatever the number of
+// thresholds -- one GEMM pass plus 4 B per pair of HBM traffic instead of one full GEMM per 63
+// thresholds.
 int count_slabs(const EvalWs& w, int Q, const PrepView& b, const int* b_gidx, const int* thr_ofs, const int* thr_cnt,
                 const float* thr_val, const int* thr_gidx, unsigned* counts, int max_cnt, cudaStream_t stream) {
-  for (int m0 = 0; m0 < Q; m0 += kSlabRows) {
-    const int rows = Q - m0 < kSlabRows ? Q - m0 : kSlabRows;
+  for (int m0 = 0; m0 < Q; m0 += w.slab_rows) {
+    const int rows = Q - m0 < w.slab_rows ? Q - m0 : w.slab_rows;
     const PrepView a = sub_rows(w.a, m0, rows);
     for (int c0 = 0; c0 < b.rows; c0 += w.slab_ld) {
       const int cols = b.rows - c0 < w.slab_ld ? b.rows - c0 : w.slab_ld;
@@ -175,15 +183,17 @@ int count_slabs(const EvalWs& w, int Q, const PrepView& b, const int* b_gidx, co
       ep.M = rows;
       ep.mode = DIST_SQ;
       ep.rowmax_key = nullptr;
-      ep.run_flag = w.blk_flag + (m0 >> 8);
+      ep.run_flag = w.slab_any + m0 / w.slab_rows;   // no flagged block in this slab: the launch returns at once
       GemmOperands ops;
       if (rows > kBM) {
         DEMO_TRY(make_gemm2_operands(a, bc, &ops));
-        const Schedule s = make_dense_schedule2(rows, cols);
+        Schedule s = make_dense_schedule2(rows, cols);
+        s.m_skip = w.blk_unflag + (m0 >> 8);          // unflagged blocks are counted by the GEMM epilogue
         DEMO_TRY(launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream));
       } else {
         DEMO_TRY(make_gemm_operands(a, bc, &ops));
-        const Schedule s = make_dense_schedule(rows, cols);
+        Schedule s = make_dense_schedule(rows, cols);
+        s.m_skip = w.blk_unflag + (m0 >> 8);
         DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
       }
       CountRows cr;
@@ -208,7 +218,8 @@ int count_features(const EvalWs& w, int Q, int g0, int gn, const int* thr_ofs, c
   // Rows with more than one window of thresholds: their 256-row query blocks go to the slab path
   // (when the workspace holds a slab), everything else is counted in the GEMM epilogue.
   const bool use_slab = max_cnt > kWin && w.slab != nullptr;
-  if (use_slab) DEMO_TRY(launch_block_flags(thr_cnt, Q, kWin, w.blk_flag, stream));
+  if (use_slab)
+    DEMO_TRY(launch_block_flags(thr_cnt, Q, kWin, w.slab_rows / 256, w.blk_flag, w.blk_unflag, w.slab_any, stream));
   GemmOperands ops;
   DEMO_TRY(make_gemm_operands(w.a, b, &ops));
   EpiCount::Params ep;

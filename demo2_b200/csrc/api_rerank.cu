@@ -32,6 +32,47 @@ size_t carve_rr(Carver& c, int N, int Q, int d, int k1, int k2, RrWs* w) {
   return c.off;
 }
 
+// One launch of the store GEMM over A rows x B rows of the SAME feature set (global offsets a0 /
+// b0), restricted to the tiles that hold an element with global row <= global column.  The value
+// of a pair is the GEMM result with the lower index on the A side (EpiStore::Params), whatever
+// the tiling or sharding: the full matrix is produced from its upper triangle (half the MMA work)
+// and a row shard from two launches, bit-identically.
+int launch_sym_store(const PrepView& a, int a0, const PrepView& b, int b0, EpiStore::Params ep, cudaStream_t stream) {
+  ep.a_norm = a.norm;
+  ep.a_inv = a.inv_scale;
+  ep.b_norm = b.norm;
+  ep.b_inv = b.inv_scale;
+  ep.M = a.rows;
+  ep.mode = DIST_SQ;
+  ep.a_global0 = a0;
+  ep.b_global0 = b0;
+  GemmOperands ops;
+  if (prefer_pair_kernel(a.rows, b.rows)) {
+    DEMO_TRY(make_gemm2_operands(a, b, &ops));
+    Schedule s = make_dense_schedule2(a.rows, b.rows);
+    s.tri = 1;
+    s.tri_a0 = a0;
+    s.tri_b0 = b0;
+    return launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream);
+  }
+  DEMO_TRY(make_gemm_operands(a, b, &ops));
+  Schedule s = make_dense_schedule(a.rows, b.rows);
+  s.tri = 1;
+  s.tri_a0 = a0;
+  s.tri_b0 = b0;
+  return launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream);
+}
+
+PrepView row_range(const PrepView& v, int row0, int nrows) {
+  PrepView s = v;
+  s.hi = v.hi + static_cast<size_t>(row0) * 2 * v.pitch;
+  s.lo = s.hi + 32;
+  s.norm = v.norm + row0;
+  s.inv_scale = v.inv_scale + row0;
+  s.rows = nrows;
+  return s;
+}
+
 // Row-sharded re-ranking: workspace of one rank owning up to rows_cap rows.
 struct RrShardWs {
   PrepView a;           // all N rows prepared (features are replicated)
@@ -95,32 +136,30 @@ int demo_rerank_shard_topk(const float* feat, int N, int Q, int d, int64_t ld, i
   DEMO_TRY(launch_prep_rows(feat, N, d, ld, nm, nullptr, w.a, feat_n_out, d, stream));
   if (nrows == 0) return DEMO_OK;
   DEMO_REQUIRE(rank_rows, "rerank shard: null output");
-  PrepView rows = w.a;  // the local rows as the A operand
-  rows.hi += static_cast<size_t>(row0) * 2 * w.a.pitch;
-  rows.lo += static_cast<size_t>(row0) * 2 * w.a.pitch;
-  rows.norm += row0;
-  rows.inv_scale += row0;
-  rows.rows = nrows;
-  GemmOperands ops;
-  DEMO_TRY(make_gemm_operands(rows, w.a, &ops));
+  const PrepView rows = row_range(w.a, row0, nrows);   // the local rows
   DEMO_CHECK_CUDA(cudaMemsetAsync(w.rowmax_key, 0, sizeof(unsigned) * nrows, stream));
-  EpiStore::Params ep;
-  ep.a_norm = rows.norm;
-  ep.a_inv = rows.inv_scale;
-  ep.b_norm = w.a.norm;
-  ep.b_inv = w.a.inv_scale;
-  ep.out = w.E;
-  ep.ldo = N;
-  ep.M = nrows;
-  ep.mode = DIST_SQ;
-  ep.rowmax_key = w.rowmax_key;
-  if (prefer_pair_kernel(nrows, N)) {
-    DEMO_TRY(make_gemm2_operands(rows, w.a, &ops));
-    const Schedule s = make_dense_schedule2(nrows, N);
-    DEMO_TRY(launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream));
-  } else {
-    const Schedule s = make_dense_schedule(nrows, N);
-    DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
+  {
+    // columns j >= i: local rows on the A side, stored in place
+    EpiStore::Params ep;
+    ep.out = w.E;
+    ep.ldo = N;
+    ep.rowmax_key = w.rowmax_key;
+    ep.sym_mask = 1;
+    DEMO_TRY(launch_sym_store(rows, row0, w.a, 0, ep, stream));
+  }
+  {
+    // columns j < i: the pair's value is defined with the lower index (j) on the A side; the
+    // local rows are the B operand and every result is stored at the transposed position
+    EpiStore::Params ep;
+    ep.out = w.E;
+    ep.ldo = N;
+    ep.rowmax_key = nullptr;
+    ep.store_normal = 0;
+    ep.sym_mirror = 1;
+    ep.out_t = w.E;
+    ep.ldo_t = N;
+    ep.rowmax_key_t = w.rowmax_key;
+    DEMO_TRY(launch_sym_store(row_range(w.a, 0, row0 + nrows), 0, rows, row0, ep, stream));
   }
   keys_to_float_kernel2<<<ceil_div(nrows, 256), 256, 0, stream>>>(w.rowmax_key, w.rowmax, nrows);
   DEMO_CHECK_CUDA(cudaGetLastError());
@@ -190,28 +229,19 @@ int demo_rerank(const float* feat, int N, int Q, int d, int64_t ld, int flags, i
     DEMO_REQUIRE(feat && d > 0 && ld >= d, "rerank: bad features");
     const int nm = (flags & DEMO_FLAG_L2NORM) ? PREP_NORM_F_NORMALIZE : PREP_NORM_NONE;
     DEMO_TRY(launch_prep_rows(feat, N, d, ld, nm, nullptr, w.a, feat_n_out, d, stream));
-    GemmOperands ops;
-    DEMO_TRY(make_gemm_operands(w.a, w.a, &ops));
     const bool fused_max = local_distmat == nullptr;
     if (fused_max) DEMO_CHECK_CUDA(cudaMemsetAsync(w.rowmax_key, 0, sizeof(unsigned) * N, stream));
+    // upper triangle only; every result is also stored at its transposed position
     EpiStore::Params ep;
-    ep.a_norm = w.a.norm;
-    ep.a_inv = w.a.inv_scale;
-    ep.b_norm = w.a.norm;
-    ep.b_inv = w.a.inv_scale;
     ep.out = w.E;
     ep.ldo = N;
-    ep.M = N;
-    ep.mode = DIST_SQ;
     ep.rowmax_key = fused_max ? w.rowmax_key : nullptr;
-    if (prefer_pair_kernel(N, N)) {
-      DEMO_TRY(make_gemm2_operands(w.a, w.a, &ops));
-      const Schedule s = make_dense_schedule2(N, N);
-      DEMO_TRY(launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream));
-    } else {
-      const Schedule s = make_dense_schedule(N, N);
-      DEMO_TRY(launch_sqdist_gemm<EpiStore>(ops, s, s.num_units, ep, stream));
-    }
+    ep.sym_mask = 1;
+    ep.sym_mirror = 1;
+    ep.out_t = w.E;
+    ep.ldo_t = N;
+    ep.rowmax_key_t = fused_max ? w.rowmax_key : nullptr;
+    DEMO_TRY(launch_sym_store(w.a, 0, w.a, 0, ep, stream));
     if (fused_max) {
       keys_to_float_kernel2<<<ceil_div(N, 256), 256, 0, stream>>>(w.rowmax_key, w.rowmax, N);
     } else {

@@ -75,6 +75,18 @@ struct EpiStore {
     int mode;
     unsigned* rowmax_key;  // optional: per-row max of the stored values (ordered-uint keys)
     const unsigned char* run_flag = nullptr;  // optional (device): the launch is a no-op when *run_flag == 0
+    // Symmetric all-pairs matrices (A and B are row ranges of the SAME set, global indices
+    // a_global0 + r / b_global0 + c).  The value of a pair is DEFINED as the GEMM result with the
+    // lower index on the A side, so that it does not depend on how the matrix is tiled or sharded:
+    //   store_normal  out[r][c] = v          (only where gr <= gc when sym_mask is set)
+    //   sym_mirror    out_t[c][r] = v        where gr < gc (the transposed position; lanes are
+    //                 consecutive rows r, so every store instruction writes one 128-byte line)
+    // rowmax_key_t receives the maxima of the mirrored stores (per column c).
+    int store_normal = 1, sym_mask = 0, sym_mirror = 0;
+    int a_global0 = 0, b_global0 = 0;
+    float* out_t = nullptr;
+    long long ldo_t = 0;
+    unsigned* rowmax_key_t = nullptr;
   };
   const Params& p;
   EpiColumns cols;
@@ -95,6 +107,8 @@ struct EpiStore {
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0);
     const float2* col = cols.s_col + as * kBN + col0;
     const int n_here = t.n_valid - col0;  // valid columns in this thread's half
+    const int gr = p.a_global0 + row;                 // global index of this thread's row
+    const int gc0 = p.b_global0 + t.n0 + col0;        // global index of this thread's first column
     float vmax = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < kEpiCols / 32; ++c) {
@@ -103,7 +117,6 @@ struct EpiStore {
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-row branches
       tmem_ld_32x32(taddr + c * 32, r);
       tmem_ld_wait();
-      if (!row_ok) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -116,19 +129,42 @@ struct EpiStore {
         }
       }
       const int nv = min(32, n_here - c * 32);
-      if (nv == 32 && vec_ok) {
+      if (p.store_normal && row_ok) {
+        const int gc = gc0 + c * 32;                  // column j of this chunk has global index gc + j
+        const bool all_upper = !p.sym_mask || gr <= gc;
+        if (nv == 32 && vec_ok && all_upper) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.rowmax_key) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nv) orow[c * 32 + j] = v[j];
+            for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv && (!p.sym_mask || gr <= gc + j)) {
+              orow[c * 32 + j] = v[j];
+              vmax = fmaxf(vmax, v[j]);
+            }
+        }
       }
-      if (p.rowmax_key) {
+      if (p.sym_mirror) {
+        // transposed position: out_t[gc + j - b_global0 ...]; addressed by operand-local indices
+        const int gc = gc0 + c * 32;
+        float* tcol = p.out_t + static_cast<long long>(t.n0 + col0 + c * 32) * p.ldo_t + row;
+        if (__any_sync(0xffffffffu, row_ok && gr < gc + nv - 1 + 1)) {   // some lane has an element above the diagonal
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nv) vmax = fmaxf(vmax, v[j]);
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = row_ok && j < nv && gr < gc + j;
+            if (ok) tcol[static_cast<long long>(j) * p.ldo_t] = v[j];
+            if (p.rowmax_key_t) {
+              const unsigned key = ok ? float_key(v[j]) : 0u;
+              const unsigned m = __reduce_max_sync(0xffffffffu, key);
+              if (m != 0u && (threadIdx.x & 31) == 0) atomicMax(p.rowmax_key_t + t.n0 + col0 + c * 32 + j, m);
+            }
+          }
+        }
       }
     }
     if (p.rowmax_key && row_ok && vmax > -INFINITY) atomicMax(p.rowmax_key + row, float_key(vmax));

@@ -64,6 +64,9 @@ struct Schedule {
   // Optional per-256-row-block flags (device): units of a flagged A block are empty for this launch
   // (the fused rank count leaves query blocks with more thresholds than one window to the slab path).
   const unsigned char* m_skip = nullptr;
+  // Symmetric all-pairs problems (A and B are row ranges of one set with global offsets tri_a0 /
+  // tri_b0): tiles that hold no element with (global row) <= (global column) are empty.
+  int tri = 0, tri_a0 = 0, tri_b0 = 0;
 };
 
 __device__ __forceinline__ int schedule_num_units(const Schedule& s) {
@@ -104,6 +107,7 @@ __device__ __forceinline__ WorkUnit schedule_get(const Schedule& s, int u) {
     w.n_rows = e.z;
   }
   if (s.m_skip != nullptr && __ldg(s.m_skip + (w.m0 >> 8)) != 0) w.n_rows = 0;
+  if (s.tri && s.tri_a0 + w.m0 > s.tri_b0 + w.n0 + w.n_rows - 1) w.n_rows = 0;
   return w;
 }
 

@@ -133,14 +133,17 @@ prep_rows_vec_kernel(const float* __restrict__ x, int rows, int d, long long ldx
 }
 
 // Streaming variant for rows that live in pinned HOST memory (zero-copy: the loads go over PCIe).
-// A small grid of 64-thread blocks walks the rows with a grid stride; at <= 80 registers per
+// A small grid of 64-thread blocks walks the rows with a grid stride; at <= 72 registers per
 // thread two such blocks fit on an SM NEXT TO a resident CTA of the count GEMM (384 threads x 137
-// registers, 205 KB of shared memory), so a slab of the gallery can be pulled in and prepared
+// registers, 200 KB of shared memory), so a slab of the gallery can be pulled in and prepared
 // while the tensor cores rank the previous slab.  PCIe needs ~0.2 MB in flight; the grid keeps
-// (2 warps x 6 KB) x blocks = several MB.
+// (2 warps x 6 KB) x blocks = several MB.  The kernel asks for the SAME shared-memory carve-out
+// as the GEMM (maximum shared memory): an SM cannot change its L1 / shared split while blocks are
+// resident, so with the default preference a GEMM CTA had to wait until every streaming block of
+// that SM had left (measured: the two kernels ran one after the other, 120 ms instead of 67).
 constexpr int kStreamWarps = 2;
 template <int kNV>
-__global__ void __launch_bounds__(kStreamWarps * 32, 12)
+__global__ void __launch_bounds__(kStreamWarps * 32, 14)
 prep_rows_stream_kernel(const float* __restrict__ x, int rows, int d, long long ldx, int norm_mode,
                         const int* __restrict__ perm, __half* __restrict__ hi, __half* __restrict__ lo,
                         int pitch, float* __restrict__ norm, float* __restrict__ inv_scale,
@@ -225,12 +228,22 @@ int launch_prep_rows(const float* x, int rows, int d, long long ldx, int norm_mo
     static const int per_sm = getenv("DEMO_STREAM_BLOCKS") ? atoi(getenv("DEMO_STREAM_BLOCKS")) : 2;
     const int sblocks = min(ceil_div(rows, kStreamWarps), (per_sm > 0 ? per_sm : 2) * num_sms());
 #define DEMO_PREP_STREAM(NV)                                                                           \
-  prep_rows_stream_kernel<NV><<<sblocks, kStreamWarps * 32, 0, stream>>>(                              \
-      x, rows, d, ldx, norm_mode, perm, out.hi, out.lo, out.pitch, out.norm, out.inv_scale, xn_out, ldxn)
-    if (out.pitch <= 512) DEMO_PREP_STREAM(4);
-    else if (out.pitch <= 1024) DEMO_PREP_STREAM(8);
-    else if (out.pitch <= 1536) DEMO_PREP_STREAM(12);
-    else DEMO_PREP_STREAM(16);
+  {                                                                                                    \
+    static PerDeviceInt carved;                                                                        \
+    const int dev = current_device();                                                                  \
+    if (!carved.get(dev)) {                                                                            \
+      DEMO_CHECK_CUDA(cudaFuncSetAttribute(prep_rows_stream_kernel<NV>,                                \
+                                           cudaFuncAttributePreferredSharedMemoryCarveout,             \
+                                           cudaSharedmemCarveoutMaxShared));                           \
+      carved.set(dev, 1);                                                                              \
+    }                                                                                                  \
+    prep_rows_stream_kernel<NV><<<sblocks, kStreamWarps * 32, 0, stream>>>(                            \
+        x, rows, d, ldx, norm_mode, perm, out.hi, out.lo, out.pitch, out.norm, out.inv_scale, xn_out, ldxn); \
+  }
+    if (out.pitch <= 512) DEMO_PREP_STREAM(4)
+    else if (out.pitch <= 1024) DEMO_PREP_STREAM(8)
+    else if (out.pitch <= 1536) DEMO_PREP_STREAM(12)
+    else DEMO_PREP_STREAM(16)
 #undef DEMO_PREP_STREAM
     DEMO_CHECK_CUDA(cudaGetLastError());
     return DEMO_OK;

@@ -573,19 +573,32 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
 }
 
 namespace {
-__global__ void block_flags_kernel(const int* __restrict__ thr_cnt, int Q, int win, unsigned char* __restrict__ flag) {
-  const int b = blockIdx.x;
-  int any = 0;
-  for (int i = b * 256 + threadIdx.x; i < min(Q, (b + 1) * 256); i += blockDim.x) any |= thr_cnt[i] > win ? 1 : 0;
-  any = __syncthreads_or(any);
-  if (threadIdx.x == 0) flag[b] = any ? 1 : 0;
+// one CTA per slab of `bps` 256-row query blocks
+__global__ void block_flags_kernel(const int* __restrict__ thr_cnt, int Q, int win, int bps,
+                                   unsigned char* __restrict__ flag, unsigned char* __restrict__ unflag,
+                                   unsigned char* __restrict__ slab_any) {
+  const int nb = ceil_div(Q, 256);
+  int slab = 0;
+  for (int b = blockIdx.x * bps; b < min(nb, (blockIdx.x + 1) * bps); ++b) {
+    int any = 0;
+    for (int i = b * 256 + threadIdx.x; i < min(Q, (b + 1) * 256); i += blockDim.x) any |= thr_cnt[i] > win ? 1 : 0;
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) {
+      flag[b] = any ? 1 : 0;
+      unflag[b] = any ? 0 : 1;
+    }
+    slab |= any;
+  }
+  if (threadIdx.x == 0) slab_any[blockIdx.x] = slab ? 1 : 0;
 }
 }  // namespace
 
-// flag[b] = 1 when a row of the 256-row query block b has more than `win` thresholds
-int launch_block_flags(const int* thr_cnt, int Q, int win, unsigned char* flag, cudaStream_t stream) {
+// flag[b] = 1 (unflag[b] = 0) when a row of the 256-row query block b has more than `win`
+// thresholds; slab_any[s] = 1 when one of the `bps` blocks of slab s is flagged
+int launch_block_flags(const int* thr_cnt, int Q, int win, int bps, unsigned char* flag, unsigned char* unflag,
+                       unsigned char* slab_any, cudaStream_t stream) {
   if (Q <= 0) return DEMO_OK;
-  block_flags_kernel<<<ceil_div(Q, 256), 128, 0, stream>>>(thr_cnt, Q, win, flag);
+  block_flags_kernel<<<ceil_div(ceil_div(Q, 256), bps), 256, 0, stream>>>(thr_cnt, Q, win, bps, flag, unflag, slab_any);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }

@@ -65,7 +65,8 @@ struct CountRows {
 int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_base, const int* q_perm,
                         const int* thr_ofs, const int* thr_cnt, const float* thr_val, const int* thr_gidx,
                         unsigned* counts, int Q, int max_cnt, cudaStream_t stream, const CountRows* rows = nullptr);
-int launch_block_flags(const int* thr_cnt, int Q, int win, unsigned char* flag, cudaStream_t stream);
+int launch_block_flags(const int* thr_cnt, int Q, int win, int bps, unsigned char* flag, unsigned char* unflag,
+                       unsigned char* slab_any, cudaStream_t stream);
 int launch_finalize(const int* thr_ofs, const int* thr_cnt, const int* thr_junk, const unsigned* counts,
                     const int* q_perm, int Q, int max_rank, float* cmc_out, double* map_out,
                     int* num_valid_out, double* ap_out, int* first_out, double* scratch,

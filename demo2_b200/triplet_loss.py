@@ -170,11 +170,30 @@ def fused_hard_mining(global_feat, labels, check_pk: bool = True):
 # one-launch path for training-size batches
 # ------------------------------------------------------------------------------------------------
 _SMALL_WS = {}        # device index -> zero-initialised workspace (tickets return to 0 after every launch)
-_PENDING = []         # (pinned status copy, event, description) of launches not inspected yet
+_PENDING = []         # (pinned status copy, event) of launches not inspected yet
+_STATUS_RING = {}     # device index -> (device int32 [64, 8], pinned host mirror, next slot)
+_MAX_BATCH = None
 
 
 def _small_limit() -> int:
-    return int(_lib.load().demo_triplet_loss_max_batch())
+    global _MAX_BATCH
+    if _MAX_BATCH is None:
+        _MAX_BATCH = int(_lib.load().demo_triplet_loss_max_batch())
+    return _MAX_BATCH
+
+
+def _status_slot(dev):
+    """A (device, pinned host) pair of int32[8] status words from a small ring: no allocation per call."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ring = _STATUS_RING.get(key)
+    if ring is None:
+        ring = [torch.zeros((64, 8), dtype=torch.int32, device=dev), torch.zeros((64, 8), dtype=torch.int32).pin_memory(), 0]
+        _STATUS_RING[key] = ring
+    i = ring[2]
+    ring[2] = (i + 1) % 64
+    if len(_PENDING) >= 60:          # the ring is about to wrap: drain before a slot is reused
+        check_pending_status(block=True)
+    return ring[0][i], ring[1][i]
 
 
 def _small_workspace(dev) -> torch.Tensor:
@@ -224,12 +243,11 @@ class _TripletLossFused(torch.autograd.Function):
         if lab.dtype not in (torch.int32, torch.int64):
             lab = lab.to(torch.int64)
         lab = lab.contiguous()
-        loss = torch.empty(B, dtype=torch.float32, device=dev)
-        ap = torch.empty((B, N), dtype=torch.float32, device=dev)
-        an = torch.empty((B, N), dtype=torch.float32, device=dev)
-        p_inds = torch.empty((B, N), dtype=torch.int64, device=dev)
-        n_inds = torch.empty((B, N), dtype=torch.int64, device=dev)
-        status = torch.empty(B, dtype=torch.int32, device=dev) if check else None
+        fbuf = torch.empty(B * (1 + 2 * N), dtype=torch.float32, device=dev)     # loss | dist_ap | dist_an
+        loss, ap, an = fbuf[:B], fbuf[B:B + B * N].view(B, N), fbuf[B + B * N:].view(B, N)
+        ibuf = torch.empty((2, B, N), dtype=torch.int64, device=dev)
+        p_inds, n_inds = ibuf[0], ibuf[1]
+        status, status_host = _status_slot(dev) if check else (None, None)
         ws = _small_workspace(dev)
         ptrs = (C.c_void_p * B)(*[x.data_ptr() for x in xs])
         m = -1.0 if margin is None else float(margin)
@@ -237,13 +255,12 @@ class _TripletLossFused(torch.autograd.Function):
                                              m, float(hard_factor), ptr(loss), ptr(ap), ptr(an), ptr(p_inds), ptr(n_inds),
                                              ptr(status), ptr(ws), ws.numel(), stream_ptr()))
         if check == "now":
-            _raise_for_status(int(status.max().item()), "")
+            _raise_for_status(int(status[:B].max().item()), "")
         elif check:
-            host = torch.empty(B, dtype=torch.int32, pin_memory=True)
-            host.copy_(status, non_blocking=True)
+            status_host.copy_(status, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-            _PENDING.append((host, ev))
+            _PENDING.append((status_host[:B], ev))
         ctx.save_for_backward(ap, an, p_inds, n_inds, *xs)
         ctx.margin, ctx.hard_factor = m, float(hard_factor)
         ctx.mark_non_differentiable(p_inds, n_inds)

@@ -13,7 +13,12 @@ from tests.helpers import (compare_ranks_outside_near_ties, load_golden, make_ca
 pytestmark = pytest.mark.gpu
 
 DIST_RTOL, DIST_ATOL = 1e-5, 2e-6   # BASELINE.json: 1e-5 relative (+ absolute floor for ~0 entries)
-XGEMM_METRIC_ATOL = 5e-6            # see tests/test_oracle_golden.py
+# Against the REFERENCE's metrics (another fp32 GEMM: MKL there, tcgen05 here).  Measured on B200
+# over the six golden cases (profiles/parity_r2.txt): CMC identical, first-match rank identical for
+# every query, |dmAP| <= 3.1e-6 (5 near-tied positives of one case swap places; on the queries
+# without near-ties the ranks are EXACT, test_rank_indices_exact_outside_near_ties).
+XGEMM_METRIC_ATOL = 5e-6
+XGEMM_CMC_ATOL = 1e-6               # north_star: CMC within 1e-6 absolute
 
 
 @pytest.fixture(scope="module")
@@ -133,8 +138,8 @@ def test_fused_feature_eval(M, shape, seed, giq):
     assert abs(res.mAP - mAP_o) < 1e-12
     g = load_golden("eval_%s_s%d%s" % (shape, seed, "_giq" if giq else ""))
     assert abs(res.mAP - float(g["mAP"])) < XGEMM_METRIC_ATOL
-    np.testing.assert_allclose(res.cmc, g["cmc"], atol=2.5 / len(qp))
-    assert (res.first.cpu().numpy() != g["first"]).mean() < 0.01
+    np.testing.assert_allclose(res.cmc, g["cmc"], atol=XGEMM_CMC_ATOL)
+    assert (res.first.cpu().numpy() != g["first"]).mean() <= 0.002
 
 
 @pytest.mark.parametrize("shape,seed,giq", [("rgbnt201", 0, False), ("rgbnt201", 1, False), ("rgbnt201", 2, False),
@@ -229,6 +234,8 @@ def test_evaluator_drop_in(M):
     assert isinstance(distmat, np.ndarray) and distmat.shape == (836, 836)
     assert len(rpids) == 1672 and qf.shape == (836, 1536)
     assert abs(mAP - float(g["plain_mAP"])) < XGEMM_METRIC_ATOL
+    write_parity_report("evaluator_rgbnt201_s0_sigma5", {"dmAP": float(abs(mAP - float(g["plain_mAP"]))),
+                                                         "dcmc_max": float(np.abs(cmc - g["plain_cmc"]).max())})
     np.testing.assert_allclose(cmc, g["plain_cmc"], atol=2.5 / 836)
     si = sample_index(*distmat.shape)
     np.testing.assert_allclose(distmat.ravel()[si], g["plain_dist_sample"], rtol=DIST_RTOL, atol=DIST_ATOL)
