@@ -210,7 +210,7 @@ int count_slabs(const EvalWs& w, int Q, const PrepView& b, const int* b_gidx, co
 // counts[] += #{gallery rows [g0, g0 + gn) (sorted order) lexicographically before each threshold}
 int count_features(const EvalWs& w, int Q, int g0, int gn, const int* thr_ofs, const int* thr_cnt,
                    const float* thr_val, const int* thr_gidx, unsigned* counts, int max_cnt, int chunk_tiles,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int reserve_sms = 0) {
   if (gn <= 0) return DEMO_OK;
   const PrepView b = sub_rows(w.b, g0, gn);
   const int* b_gidx = w.b_gidx + g0;
@@ -240,7 +240,11 @@ int count_features(const EvalWs& w, int Q, int g0, int gn, const int* thr_ofs, c
   static const bool force_1cta = getenv("DEMO_COUNT_1CTA") != nullptr;
   const bool pair = !force_1cta && Q > kBM;
   const int n_tiles = ceil_div(G, kBN), m_blocks = ceil_div(Q, pair ? 2 * kBM : kBM);
-  const int workers = pair ? num_sms() / 2 : num_sms();
+  // reserve_sms: SMs the CTA-pair grid leaves free (the streamed evaluation pulls the next gallery
+  // slab over PCIe with a small kernel meanwhile; next to a full persistent grid it starves)
+  if (reserve_sms < 0) reserve_sms = 0;
+  const int max_pairs = pair && reserve_sms > 0 ? (num_sms() / 2 - (reserve_sms + 1) / 2 > 8 ? num_sms() / 2 - (reserve_sms + 1) / 2 : 8) : 0;
+  const int workers = pair ? (max_pairs > 0 ? max_pairs : num_sms() / 2) : num_sms();
   if (const char* e = getenv("DEMO_CHUNK_TILES")) chunk_tiles = atoi(e);  // experiments
   const bool auto_chunk = chunk_tiles <= 0;
   if (auto_chunk) {
@@ -256,7 +260,7 @@ int count_features(const EvalWs& w, int Q, int g0, int gn, const int* thr_ofs, c
   Schedule s2 = s;
   if (pair) {
     DEMO_TRY(make_gemm2_operands(w.a, b, &ops2));
-    s2 = make_chunked_schedule2(Q, G, chunk_tiles, w.a.pitch);
+    s2 = make_chunked_schedule2(Q, G, chunk_tiles, w.a.pitch, workers);
     if (use_slab) s2.m_skip = w.blk_flag;
     // Paced schedule (gemm_sm100.cuh, Schedule::pace): a worker starts its i-th unit only when
     // every worker has issued the loads of its unit i - 2.  Free-running workers drift apart by
@@ -280,7 +284,7 @@ int count_features(const EvalWs& w, int Q, int g0, int gn, const int* thr_ofs, c
   for (int wdw = 0; wdw < windows; ++wdw) {
     ep.window = no_epi ? -1 : wdw;
     DEMO_CHECK_CUDA(cudaMemsetAsync(w.ties.hdr, 0, (16 + (s2.pace ? static_cast<size_t>(s2.num_units) * s2.pace_steps + 1 : 0)) * sizeof(unsigned), stream));
-    if (pair) DEMO_TRY(launch_sqdist_gemm2<EpiCount>(ops2, s2, s2.num_units, ep, stream));
+    if (pair) DEMO_TRY(launch_sqdist_gemm2<EpiCount>(ops2, s2, s2.num_units, ep, stream, max_pairs));
     else DEMO_TRY(launch_sqdist_gemm<EpiCount>(ops, s, s.num_units, ep, stream));
     resolve_ties_kernel<<<2 * num_sms(), 256, 0, stream>>>(w.ties, b_gidx, thr_ofs, thr_cnt, thr_val, thr_gidx,
                                                             counts, wdw);
@@ -448,19 +452,19 @@ int demo_build_thresholds(const int* rec_ofs, const float* rec_dist, const int* 
 // path when the workspace was sized with demo_eval_workspace_bytes_ex(.., max_cnt).
 int demo_eval_count_range(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes, const int* thr_ofs,
                           const int* thr_cnt, const float* thr_val, const int* thr_gidx, unsigned* counts,
-                          int max_cnt, int chunk_tiles, int g_row0, int g_nrows, void* stream_) {
+                          int max_cnt, int chunk_tiles, int g_row0, int g_nrows, int reserve_sms, void* stream_) {
   EvalWs w;
   DEMO_REQUIRE(g_row0 >= 0 && g_nrows >= 0 && g_row0 + g_nrows <= G, "eval_count: gallery range outside [0, %d)", G);
   DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T_local, &w, max_cnt));
   return count_features(w, Q, g_row0, g_nrows, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, chunk_tiles,
-                        static_cast<cudaStream_t>(stream_));
+                        static_cast<cudaStream_t>(stream_), reserve_sms);
 }
 
 int demo_eval_count(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes, const int* thr_ofs,
                     const int* thr_cnt, const float* thr_val, const int* thr_gidx, unsigned* counts,
                     int max_cnt, int chunk_tiles, void* stream_) {
   return demo_eval_count_range(Q, G, d, T_local, ws, ws_bytes, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt,
-                               chunk_tiles, 0, G, stream_);
+                               chunk_tiles, 0, G, 0, stream_);
 }
 
 int demo_cmc_map_finalize(const int* thr_ofs, const int* thr_cnt, const int* thr_junk, const unsigned* counts,

@@ -298,14 +298,14 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
 // Operands for the CTA-pair kernel: all four tensor maps use 128-row boxes.
 int make_gemm2_operands(const PrepView& a, const PrepView& b, GemmOperands* ops);
-Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch);
+Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch, int workers = 0);
 Schedule make_dense_schedule2(int M, int N);
 bool prefer_pair_kernel(int M, int N);
 int max_active_pairs(const void* kernel, int smem);
 
 template <class Epi>
 int launch_sqdist_gemm2(const GemmOperands& ops, const Schedule& sched, int max_units,
-                        const typename Epi::Params& ep, cudaStream_t stream) {
+                        const typename Epi::Params& ep, cudaStream_t stream, int max_pairs = 0) {
   if (max_units <= 0) return DEMO_OK;
   auto kernel = sqdist_gemm2_kernel<Epi>;
   constexpr int smem = Gemm2Smem<Epi>::kTotal;
@@ -323,6 +323,7 @@ int launch_sqdist_gemm2(const GemmOperands& ops, const Schedule& sched, int max_
     if (const char* e = getenv("DEMO_PAIRS")) pairs = atoi(e) > 0 && atoi(e) < pairs ? atoi(e) : pairs;  // experiments
     pairs_of.set(dev, pairs);
   }
+  if (max_pairs > 0 && max_pairs < pairs) pairs = max_pairs;   // the caller keeps SMs free for a concurrent kernel
   const int grid = 2 * (max_units < pairs ? max_units : pairs);
   kernel<<<grid, kGemmThreads, smem, stream>>>(ops.a, ops.b, sched, ops.num_k_blocks, ep);
   DEMO_CHECK_CUDA(cudaGetLastError());

@@ -138,7 +138,8 @@ int make_gemm2_operands(const PrepView& a, const PrepView& b, GemmOperands* ops)
 }
 
 // Units of the CTA-pair kernel: 256 A rows x chunk_tiles B tiles.
-Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch) {
+Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch, int workers) {
+  if (workers <= 0) workers = num_sms() / 2;
   Schedule s;
   s.mode = 1;
   s.M = M;
@@ -148,13 +149,12 @@ Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch) {
   s.n_tiles = ceil_div(N, kBN);
   s.chunk_tiles = chunk_tiles < 1 ? 1 : chunk_tiles;
   s.n_chunks = ceil_div(s.n_tiles, s.chunk_tiles);
-  s.group_m = balanced_group_m(s.m_blocks, 2 * kBM, d_pitch, num_sms() / 2);
+  s.group_m = balanced_group_m(s.m_blocks, 2 * kBM, d_pitch, workers);
   if (const char* e = getenv("DEMO_GROUP_M")) s.group_m = atoi(e) > 0 ? atoi(e) : s.group_m;  // experiments
   s.num_units = s.m_blocks * s.n_chunks;
   // The workers / group_m pairs that read the same query block are neighbouring workers: measured
   // 10.4 instead of 17 GB of DRAM reads at 20k x 262k (same run time).  DEMO_ADJ=0: w, w + group_m.
   {
-    const int workers = num_sms() / 2;
     const char* e = getenv("DEMO_ADJ");
     if (!(e && atoi(e) == 0) && workers % s.group_m == 0) s.adj = workers / s.group_m;
   }

@@ -133,15 +133,20 @@ prep_rows_vec_kernel(const float* __restrict__ x, int rows, int d, long long ldx
 }
 
 // Streaming variant for rows that live in pinned HOST memory (zero-copy: the loads go over PCIe).
-// A small grid of 64-thread blocks walks the rows with a grid stride; at <= 72 registers per
-// thread two such blocks fit on an SM NEXT TO a resident CTA of the count GEMM (384 threads x 137
-// registers, 200 KB of shared memory), so a slab of the gallery can be pulled in and prepared
-// while the tensor cores rank the previous slab.  PCIe needs ~0.2 MB in flight; the grid keeps
-// (2 warps x 6 KB) x blocks = several MB.  The kernel asks for the SAME shared-memory carve-out
-// as the GEMM (maximum shared memory): an SM cannot change its L1 / shared split while blocks are
-// resident, so with the default preference a GEMM CTA had to wait until every streaming block of
-// that SM had left (measured: the two kernels ran one after the other, 120 ms instead of 67).
+// A SMALL grid (kStreamBlocks blocks of 64 threads) walks the rows with a grid stride, so that a
+// slab of the gallery can be pulled in and prepared while the tensor cores rank the previous slab.
+// PCIe needs ~0.2 MB in flight; 64 blocks x 2 warps x 6 KB keep 0.8 MB, and they reach the same
+// 51 GB/s as a grid that fills the machine (32 blocks: 43 GB/s, 16: 32, 8: 16).  What matters for
+// the overlap (tools/probe_stream.py --overlap-only, half of the 20k x 1M count GEMM against the
+// zero-copy prepare of the other half): a machine-filling prepare grid (2 blocks per SM) ran
+// almost back to back with the persistent GEMM grid (118 ms for 71 + 60); 64 blocks finish
+// together with it (76 ms with the GEMM on 70 CTA pairs, and in the streamed evaluation of
+// 20k x 1M the count stage takes 141 ms = the GEMM alone, whether the GEMM leaves SMs free
+// (demo_eval_count_range reserve_sms) or not).  The kernel asks for the SAME
+// shared-memory carve-out as the GEMM (maximum shared memory): an SM cannot change its L1 /
+// shared split while blocks are resident.
 constexpr int kStreamWarps = 2;
+constexpr int kStreamBlocks = 64;
 template <int kNV>
 __global__ void __launch_bounds__(kStreamWarps * 32, 14)
 prep_rows_stream_kernel(const float* __restrict__ x, int rows, int d, long long ldx, int norm_mode,
@@ -225,8 +230,8 @@ int launch_prep_rows(const float* x, int rows, int d, long long ldx, int norm_mo
       x, rows, d, ldx, norm_mode, perm, out.hi, out.lo, out.pitch, out.norm, out.inv_scale, xn_out, ldxn)
   if (host_input && vec) {
     // zero-copy rows: small persistent grid (see prep_rows_stream_kernel)
-    static const int per_sm = getenv("DEMO_STREAM_BLOCKS") ? atoi(getenv("DEMO_STREAM_BLOCKS")) : 2;
-    const int sblocks = min(ceil_div(rows, kStreamWarps), (per_sm > 0 ? per_sm : 2) * num_sms());
+    static const int total_env = getenv("DEMO_STREAM_TOTAL") ? atoi(getenv("DEMO_STREAM_TOTAL")) : 0;  // experiments
+    const int sblocks = min(ceil_div(rows, kStreamWarps), total_env > 0 ? total_env : kStreamBlocks);
 #define DEMO_PREP_STREAM(NV)                                                                           \
   {                                                                                                    \
     static PerDeviceInt carved;                                                                        \

@@ -18,6 +18,7 @@ with a numpy engine standing in for the CUDA stages).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -219,11 +220,12 @@ class CudaEngine:
                                              ptr(thr_cnt), ptr(thr_val), ptr(thr_gidx), ptr(thr_junk), stream_ptr()))
         return thr_cnt, thr_val, thr_gidx, thr_junk
 
-    def count(self, w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, g_row0=0, g_nrows=None):
+    def count(self, w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, g_row0=0, g_nrows=None,
+              reserve_sms=0):
         g_nrows = w.G - g_row0 if g_nrows is None else g_nrows
         check(self.lib.demo_eval_count_range(w.Q, w.G, w.d, plan.T, ptr(w.buf), w.nbytes, ptr(thr_ofs), ptr(thr_cnt),
                                              ptr(thr_val), ptr(thr_gidx), ptr(counts), int(max_cnt), 0, int(g_row0),
-                                             int(g_nrows), stream_ptr()))
+                                             int(g_nrows), int(reserve_sms), stream_ptr()))
 
     def finalize(self, thr_ofs, thr_cnt, thr_junk, counts, q_perm, Q, max_rank):
         dev = counts.device
@@ -376,7 +378,7 @@ class ShardedEvaluator:
     # ---- host-resident inputs: the gallery is pulled in slab by slab while the GEMM ranks --------
     def evaluate_host(self, q_host, g_host_local, q_pid, g_pid_local, q_cam, g_cam_local, g_index_base: int = 0,
                       normalize: bool = False, max_rank: int = 50, timers: dict | None = None,
-                      slab_rows: int = 131072, shard_query_upload: bool = True):
+                      slab_rows: int = 131072, shard_query_upload: bool = True, reserve_sms: int | None = None):
         """One evaluation whose features live in PINNED HOST memory (what R1_mAP_eval.update
         accumulates when the model runs elsewhere, utils/metrics.py:244).  No fp32 copy of the
         gallery is made on the device: demo_eval_prepare pulls the rows over PCIe in pid-sorted
@@ -387,6 +389,8 @@ class ShardedEvaluator:
         the rest arrives over NVLink (all-gather)."""
         eng = self.engine
         assert isinstance(eng, CudaEngine), "evaluate_host needs the CUDA engine"
+        if reserve_sms is None:
+            reserve_sms = int(os.environ.get("DEMO_RESERVE_SMS", "0"))   # env: experiments
         dev = torch.device("cuda", torch.cuda.current_device())
         ev = eng.event if timers is not None else None
         mark = (lambda: ev()) if ev else (lambda: None)
@@ -455,7 +459,12 @@ class ShardedEvaluator:
                 if i > 0:
                     main.wait_event(up_events[i - 1])
                 if T > 0 and b > a:
-                    eng.count(w, plan, thr_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=a, g_nrows=b - a)
+                    # reserve_sms > 0: while later slabs are still being pulled in, the persistent GEMM
+                    # grid leaves that many SMs to the kernel that pulls them.  Measured on 20k x 1M: not
+                    # needed once the pulling grid is small (64 blocks): 189.5 ms with 0, 191.9 with 8.
+                    busy = g_host_in and i + 2 < len(bounds)
+                    eng.count(w, plan, thr_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=a, g_nrows=b - a,
+                              reserve_sms=reserve_sms if busy else 0)
                     n_count += 1
         t5 = mark()
         if self.world > 1:

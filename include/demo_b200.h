@@ -107,7 +107,9 @@ DEMO_API size_t demo_eval_matrix_workspace_bytes(int Q, int G, int64_t T);
  *                         itself, in sorted order (queried rows first), slab by slab.
  *   demo_eval_extract     records from the prepared queries + queried gallery rows; g_index
  *                         (optional, [G]) = global gallery index per local row (tie-break key).
- *   demo_eval_count_range counts against the sorted gallery rows [g_row0, g_row0+g_nrows).       */
+ *   demo_eval_count_range counts against the sorted gallery rows [g_row0, g_row0+g_nrows);
+ *                         reserve_sms > 0: the persistent GEMM grid leaves that many SMs free for
+ *                         the kernel that pulls in the next slab meanwhile.                      */
 DEMO_API int demo_eval_prepare(const float* x, int n, int d, int64_t ld, int flags, int which, int row0, int nrows,
                                const void* plan, size_t plan_bytes, int Q, int G, int64_t T, void* ws,
                                size_t ws_bytes, float* xn_out, void* stream);
@@ -117,7 +119,7 @@ DEMO_API int demo_eval_extract(int Q, int G, int d, const int* q_cam, const int*
 DEMO_API int demo_eval_count_range(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes,
                                    const int* thr_ofs, const int* thr_cnt, const float* thr_val,
                                    const int* thr_gidx, unsigned* counts, int max_cnt, int chunk_tiles,
-                                   int g_row0, int g_nrows, void* stream);
+                                   int g_row0, int g_nrows, int reserve_sms, void* stream);
 DEMO_API int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg,
                                int flags, const int* q_cam, const int* g_cam, int g_index_base,
                                const void* plan, size_t plan_bytes, int64_t T, void* ws, size_t ws_bytes,

@@ -2,8 +2,10 @@
 
     python tools/summarize_ncu.py launches gpurun_out/launches_X.csv  "header text"  > profiles/launches_X_summary.txt
     python tools/summarize_ncu.py last     gpurun_out/launches_rerank_X.csv "header text" [skip_regex]
+    ncu -i X.ncu-rep --page raw --csv > raw.csv;  python tools/summarize_ncu.py raw raw.csv "header text"
 `launches`: per-kernel call count, total device time and share.  `last`: the kernels of the last
-iteration in launch order with time and DRAM bytes (needs dram__bytes_read/write.sum in the CSV)."""
+iteration in launch order with time and DRAM bytes (needs dram__bytes_read/write.sum in the CSV).
+`raw`: the metrics DESIGN.md quotes from a `--set full` capture, one block per captured launch."""
 import csv
 import re
 import sys
@@ -22,8 +24,37 @@ def short(name):
     return name[:70]
 
 
+RAW_METRICS = [
+    "Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_size",
+    "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "sm__cycles_elapsed.avg.per_second",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_lsu.sum",
+    "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_global_op_st.sum",
+]
+
+
+def raw(path, header):
+    with open(path, newline="") as f:
+        table = list(csv.reader(l for l in f if l.startswith('"')))
+    hdr, units = table[0], table[1]
+    print("# " + header)
+    for vals in table[2:]:
+        print("----")
+        for m in RAW_METRICS:
+            if m in hdr:
+                i = hdr.index(m)
+                print("%s = %s %s" % (m, vals[i], units[i]))
+
+
 def main():
     mode, path, header = sys.argv[1], sys.argv[2], sys.argv[3]
+    if mode == "raw":
+        return raw(path, header)
     rs = rows(path)
     print("# " + header)
     if mode == "launches":
