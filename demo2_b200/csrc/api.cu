@@ -20,6 +20,26 @@ int norm_mode_of(int flags) {
   return PREP_NORM_NONE;
 }
 
+// rows longer than the validated range of the tensor-core path go to the fp32 FMA kernel
+int sqdist_flags(int flags, int d) { return d > kMaxCompensatedDim ? (flags | DEMO_FLAG_SIMT) : flags; }
+
+// row maxima of a stored matrix (SIMT path only; the tensor-core epilogue fuses them)
+__global__ void __launch_bounds__(256) rowmax_kernel(const float* __restrict__ m, long long ld, int cols,
+                                                     float* __restrict__ out) {
+  const float* row = m + static_cast<long long>(blockIdx.x) * ld;
+  float v = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) v = fmaxf(v, row[c]);
+  __shared__ float s[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) v = fmaxf(v, s[w]);
+    out[blockIdx.x] = v;
+  }
+}
+
 struct SqdistWs {
   PrepView a, b;
   unsigned* rowmax_keys;
@@ -55,7 +75,7 @@ int demo_device_ok(void) {
 
 size_t demo_sqdist_workspace_bytes(int Q, int G, int d, int flags) {
   Carver c(nullptr, ~size_t(0));
-  return round_up(carve_sqdist(c, Q, G, d, flags, nullptr), size_t(1024));
+  return round_up(carve_sqdist(c, Q, G, d, sqdist_flags(flags, d), nullptr), size_t(1024));
 }
 
 int demo_sqdist_f32(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg,
@@ -66,6 +86,7 @@ int demo_sqdist_f32(const float* q, const float* g, int Q, int G, int d, int64_t
   if (Q == 0 || G == 0) return DEMO_OK;
   DEMO_REQUIRE(q && g && out && workspace, "sqdist: null pointer");
   DEMO_REQUIRE(ldq >= d && ldg >= d && ldo >= G, "sqdist: leading dimension too small");
+  flags = sqdist_flags(flags, d);
   Carver c(workspace, workspace_bytes);
   SqdistWs w;
   carve_sqdist(c, Q, G, d, flags, &w);
@@ -84,7 +105,10 @@ int demo_sqdist_f32(const float* q, const float* g, int Q, int G, int d, int64_t
     const bool use_n = nm != PREP_NORM_NONE;
     DEMO_TRY(launch_simt_dist(use_n ? qn : q, use_n ? gn : g, Q, G, d, use_n ? d : ldq, use_n ? d : ldg,
                               w.a.norm, w.b.norm, out, ldo, mode, stream));
-    DEMO_REQUIRE(rowmax == nullptr, "sqdist: rowmax is not supported on the SIMT path");
+    if (rowmax) {
+      rowmax_kernel<<<Q, 256, 0, stream>>>(out, ldo, G, rowmax);
+      DEMO_CHECK_CUDA(cudaGetLastError());
+    }
     return DEMO_OK;
   }
   if (rowmax) DEMO_CHECK_CUDA(cudaMemsetAsync(w.rowmax_keys, 0, sizeof(unsigned) * Q, stream));

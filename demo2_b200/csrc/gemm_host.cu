@@ -152,11 +152,15 @@ Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch, int 
   s.group_m = balanced_group_m(s.m_blocks, 2 * kBM, d_pitch, workers);
   if (const char* e = getenv("DEMO_GROUP_M")) s.group_m = atoi(e) > 0 ? atoi(e) : s.group_m;  // experiments
   s.num_units = s.m_blocks * s.n_chunks;
-  // The workers / group_m pairs that read the same query block are neighbouring workers: measured
-  // 10.4 instead of 17 GB of DRAM reads at 20k x 262k (same run time).  DEMO_ADJ=0: w, w + group_m.
+  // Neighbour order: the workers / group_m pairs that read the same query block are neighbouring
+  // workers (w, w + 1) instead of w, w + group_m.  Measured DRAM reads per launch (run time equal
+  // within 1 %): 20k x 262k 10.4 GB against 17.1 GB, but 20k x 1M 70.6 GB against 51.9 GB
+  // (profiles/traffic_schedules_r2.txt) -- so it is used for galleries up to 512k rows only.
+  // DEMO_ADJ=0 / 1 forces it off / on.
   {
     const char* e = getenv("DEMO_ADJ");
-    if (!(e && atoi(e) == 0) && workers % s.group_m == 0) s.adj = workers / s.group_m;
+    const bool on = e ? atoi(e) != 0 : N <= (1 << 19);
+    if (on && workers % s.group_m == 0) s.adj = workers / s.group_m;
   }
   return s;
 }

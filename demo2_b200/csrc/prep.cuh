@@ -25,6 +25,12 @@ struct PrepView {
 
 inline int prep_pitch(int d) { return round_up(d, 64); }
 
+// Largest feature dimension for which the accumulation-bias compensation of prep.cu is validated
+// (tests: near-duplicate rows within 1e-5 of the fp64 distance for d = 64 .. 2048; the bias grows
+// with the number of tcgen05.mma accumulation steps, 3 * d / 16).  demo_sqdist_f32 routes longer
+// rows to the fp32 FMA kernel (the north_star's "FFMA fallback").
+constexpr int kMaxCompensatedDim = 2048;
+
 // Bytes of a prepared operand and its carve-up (same function sizes and slices).
 inline size_t prep_carve(Carver& c, int rows, int d, PrepView* v) {
   PrepView t;

@@ -2,6 +2,8 @@
 // matrix, and CMC/mAP finalisation.  See rank.cuh for the pipeline.
 #include "rank.cuh"
 
+#include <cstdlib>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -348,8 +350,8 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
   const int tbase = thr_ofs[i] + window * kCmWin;
   const int nthr = max(0, min(kCmWin, thr_cnt[i] - window * kCmWin));
   if (nthr == 0) return;
-  // rows with <= 63 finite thresholds belong to count_matrix63_kernel
-  if (skip_small && thr_cnt[i] <= 63 && isfinite(thr_val[thr_ofs[i] + thr_cnt[i] - 1])) return;
+  // rows with <= 255 finite thresholds belong to count_matrix63_kernel / count_matrix255_kernel
+  if (thr_cnt[i] <= 255 && isfinite(thr_val[thr_ofs[i] + thr_cnt[i] - 1])) return;
   for (int k = t; k < nthr; k += kCmThreads) {
     s_thr[k] = thr_val[tbase + k];
     s_tg[k] = thr_gidx[tbase + k];
@@ -544,6 +546,180 @@ count_matrix63_kernel(const float* __restrict__ distmat, long long ld, int G, in
   }
 }
 
+
+// Rows with 64 .. 255 finite thresholds (identities with a few hundred gallery images, e.g.
+// RGBNT100's ~171 per id), and shorter rows when the u16 kernel above cannot be used.  A bisection
+// over 255 slots would cost five dependent shared-memory probes at random addresses; instead the
+// value range [t_0, t_last] of the row's thresholds is cut into kC8Fine equal bins by ONE monotone
+// arithmetic map f(x) = min(F-1, int((x - t_0) * s)): thresholds and elements go through the same
+// expression, so f(thr) < f(x) implies thr < x and f(thr) > f(x) implies thr > x -- only the
+// thresholds that share the element's bin are compared explicitly, and an element can only tie
+// with a threshold of its own bin.  Common case, branch-free: one u16 table entry (first threshold
+// of the bin | how many), one probe of that threshold, a private u8 histogram column (no atomics;
+// flushed into u32 totals every 240 elements per thread, before a counter can wrap).  Bins with
+// two or more thresholds and bit-ties take a slow path (bisection inside the bin + the
+// (distance, index) rule).  4 B per pair read once.
+constexpr int kC8Threads = 256;
+constexpr int kC8Fine = 2048;
+constexpr int kC8Bins = 256;
+constexpr int kC8FlushIters = 30;   // 8 elements per thread and iteration: 240 (+ head / tail / remainder <= 10) <= 255
+
+__global__ void __launch_bounds__(kC8Threads, 4)
+count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
+                       const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
+                       const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
+                       const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int small_too,
+                       int hist_rows, CountRows rows) {
+  extern __shared__ __align__(16) unsigned char s_hist8[];   // [hist_rows][256] u8, column = thread (>= 33 rows: scratch)
+  __shared__ float s_thr[kC8Bins];                           // padded with +inf
+  __shared__ int s_tg[kC8Bins];
+  __shared__ unsigned short s_fine[kC8Fine];                 // first threshold of the bin | count << 8
+  __shared__ unsigned s_tot[kC8Bins];
+  __shared__ unsigned s_warp[kC8Threads / 32];
+  const int i = rows.row0 + blockIdx.x, t = threadIdx.x;     // i: sorted query
+  if (rows.blk_flag && rows.blk_flag[i >> 8] == 0) return;   // block handled by the fused GEMM epilogue
+  const int nthr = thr_cnt[i];
+  if (nthr <= 0 || nthr > kC8Bins - 1 || nthr >= hist_rows) return;   // longer rows: count_matrix_kernel
+  if (nthr <= kCfWin && !small_too) return;                  // count_matrix63_kernel
+  const int tbase = thr_ofs[i];
+  if (!isfinite(__ldg(thr_val + tbase + nthr - 1))) return;
+  s_thr[t] = t < nthr ? __ldg(thr_val + tbase + t) : INFINITY;
+  s_tg[t] = t < nthr ? __ldg(thr_gidx + tbase + t) : -1;
+  s_tot[t] = 0u;
+  __syncthreads();
+  const float tmin = s_thr[0], tmax = s_thr[nthr - 1];
+  const float scale = tmax > tmin ? static_cast<float>(kC8Fine) / (tmax - tmin) : 0.f;
+  auto fine_of = [&](float x) -> int {   // monotone in x for x >= tmin
+    return min(kC8Fine - 1, __float2int_rz((x - tmin) * scale));
+  };
+  // first[j] = index of the first threshold whose bin is >= j (scratch: the histogram area): thread k
+  // owns the bins (f(t_{k-1}), f(t_k)]; f(t_0) = 0 and every bin above f(t_last) gets nthr
+  unsigned* first = reinterpret_cast<unsigned*>(s_hist8);
+  if (t < nthr) {
+    const int jk = fine_of(s_thr[t]);
+    const int jp = t > 0 ? fine_of(s_thr[t - 1]) : -1;
+    for (int j = jp + 1; j <= jk; ++j) first[j] = static_cast<unsigned>(t);
+  }
+  if (t == 0)
+    for (int j = fine_of(tmax) + 1; j <= kC8Fine; ++j) first[j] = static_cast<unsigned>(nthr);
+  __syncthreads();
+  for (int j = t; j < kC8Fine; j += kC8Threads)
+    s_fine[j] = static_cast<unsigned short>(first[j] | ((first[j + 1] - first[j]) << 8));
+  __syncthreads();
+  {
+    uint4* h = reinterpret_cast<uint4*>(s_hist8);
+    for (int k = t; k < hist_rows * kC8Threads / 16; k += kC8Threads) h[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+
+  // private column: lanes of a warp on distinct banks, the four warps of a group share words
+  const uint32_t col = 4u * (t & 31) + ((t >> 5) & 3) + 128u * (t >> 7);
+  const uint32_t hist0 = smem_u32(s_hist8) + col;
+  const float* row = distmat + static_cast<long long>(q_perm ? q_perm[i] : static_cast<int>(blockIdx.x)) * ld;
+
+  // branch-free part: slot of the element, or "needs the slow path" (bit 31)
+  auto fast_pos = [&](float d) -> unsigned {
+    const unsigned e = d >= tmin ? s_fine[fine_of(d)] : 0u;
+    const unsigned base = e & 0xffu, nin = e >> 8;
+    const float tv = s_thr[base];              // first threshold of the bin (a later one, > d, when the bin is empty)
+    unsigned pos = base + ((nin != 0u && tv <= d) ? 1u : 0u);
+    pos |= (nin > 1u || tv == d) ? 0x80000000u : 0u;
+    return d > tmax ? static_cast<unsigned>(nthr) : pos;   // after every threshold: bin nthr, part of no count
+  };
+  // bins with several thresholds, bit-ties: bisection inside the bin + the (distance, index) rule
+  auto slow_pos = [&](float d, int g) -> unsigned {
+    const unsigned e = s_fine[fine_of(d)];
+    int lo = static_cast<int>(e & 0xffu), hi = lo + static_cast<int>(e >> 8);
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_thr[mid] <= d) lo = mid + 1; else hi = mid;
+    }
+    int pos = lo;
+    if (pos > 0 && s_thr[pos - 1] == d) {
+      const int gi = rows.col_gidx ? __ldg(rows.col_gidx + g) : g_index_base + g;
+      while (pos > 0 && s_thr[pos - 1] == d && s_tg[pos - 1] > gi) --pos;
+    }
+    return static_cast<unsigned>(pos);
+  };
+  auto bump = [&](unsigned pos) {
+    const uint32_t h = hist0 + pos * kC8Threads;
+    unsigned c;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(h));
+    c += 1u;
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(h), "r"(c));
+  };
+  auto place = [&](float d, int g) {
+    unsigned pos = fast_pos(d);
+    if (pos & 0x80000000u) pos = slow_pos(d, g);
+    bump(pos);
+  };
+  auto place4 = [&](const float4& x, int g0) {
+    const float d[4] = {x.x, x.y, x.z, x.w};
+    unsigned pos[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pos[k] = fast_pos(d[k]);
+    if ((pos[0] | pos[1] | pos[2] | pos[3]) & 0x80000000u) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (pos[k] & 0x80000000u) pos[k] = slow_pos(d[k], g0 + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bump(pos[k]);
+  };
+  auto flush = [&]() {                         // private columns -> u32 totals, columns back to zero
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
+    for (int b = warp; b <= nthr; b += kC8Threads / 32) {
+      uint2* p = reinterpret_cast<uint2*>(s_hist8 + b * kC8Threads + 8 * lane);
+      const uint2 x = *p;
+      unsigned sum = __dp4a(x.x, 0x01010101u, 0u) + __dp4a(x.y, 0x01010101u, 0u);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) s_tot[b] += sum;
+      *p = make_uint2(0u, 0u);
+    }
+    __syncthreads();
+  };
+
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(row) >> 2) & 3u);
+  const int head = min(G, (4 - mis) & 3);
+  if (t < head) place(__ldg(row + t), t);
+  const int nvec = (G - head) >> 2;
+  const float4* row4 = reinterpret_cast<const float4*>(row + head);
+  // full iterations (every thread has both vectors): the flush cadence is uniform over the block
+  const int n_full = nvec / (2 * kC8Threads);
+  int v = t, iters = 0;
+  for (int k = 0; k < n_full; ++k, v += 2 * kC8Threads) {
+    const float4 x = __ldcs(row4 + v), y = __ldcs(row4 + v + kC8Threads);
+    const int g0 = head + 4 * v;
+    place4(x, g0);             // (one batch of 8 costs more instructions: the slow-path test fires twice as often)
+    place4(y, g0 + 4 * kC8Threads);
+    if (++iters == kC8FlushIters) {
+      flush();
+      iters = 0;
+    }
+  }
+  for (; v < nvec; v += kC8Threads) {          // remainder: at most two vectors per thread
+    const float4 x = __ldcs(row4 + v);
+    place4(x, head + 4 * v);
+  }
+  const int tail0 = head + 4 * nvec;
+  if (tail0 + t < G) place(__ldg(row + tail0 + t), tail0 + t);
+  flush();
+  // counts[k] += sum_{b <= k} tot[b]: one bin per thread, block-wide inclusive scan
+  const unsigned mine = t <= nthr ? s_tot[t] : 0u;
+  unsigned incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += x;
+  }
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
+  __syncthreads();
+  for (int w = 0; w < (t >> 5); ++w) incl += s_warp[w];
+  if (t < nthr && incl) atomicAdd(counts + tbase + t, incl);
+}
+
 }  // namespace
 
 int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_base, const int* q_perm,
@@ -557,16 +733,30 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
   constexpr int smem = 64 * kCfThreads * 2;
   static PerDeviceInt configured;
   DEMO_CHECK_CUDA(ensure_dynamic_smem(configured, count_matrix63_kernel, smem));
-  const bool fast = G < (1 << 24) - 512;   // u16 private counters: at most G / 256 (+ head / tail) increments per thread
+  static const bool all255 = getenv("DEMO_COUNT255_ALL") != nullptr;   // A/B experiments: arithmetic-bin kernel for every row
+  const bool fast = !all255 && G < (1 << 24) - 512;   // u16 private counters: at most G / 256 (+ head / tail) increments per thread
   if (fast) {
     count_matrix63_kernel<<<Q, kCfThreads, smem, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
                                                           thr_val, thr_gidx, counts, rows);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
+  // rows with 64 .. 255 finite thresholds (all rows up to 255 when the u16 kernel is out of range)
+  if (max_cnt > kCfWin || !fast) {
+    // histogram rows: one per slot of the longest row this kernel takes (more resident blocks for short lists)
+    const int top = max_cnt < kC8Bins - 1 ? max_cnt : kC8Bins - 1;
+    const int hist_rows = (top + 1 + 31) / 32 * 32 < 64 ? 64 : (top + 1 + 31) / 32 * 32;   // >= 33 rows: setup scratch
+    const int smem8 = hist_rows * kC8Threads;
+    static PerDeviceInt configured8;
+    DEMO_CHECK_CUDA(ensure_dynamic_smem(configured8, count_matrix255_kernel, kC8Bins * kC8Threads));
+    count_matrix255_kernel<<<Q, kC8Threads, smem8, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
+                                                             thr_val, thr_gidx, counts, fast ? 0 : 1, hist_rows, rows);
+    DEMO_CHECK_CUDA(cudaGetLastError());
+  }
+  // everything else (longer rows, non-finite thresholds): generic windows
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kCmWin);
   for (int w = 0; w < windows; ++w) {
     count_matrix_kernel<<<Q, kCmThreads, 0, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
-                                                      thr_val, thr_gidx, counts, w, fast ? 1 : 0, rows);
+                                                      thr_val, thr_gidx, counts, w, 0, rows);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
   return DEMO_OK;

@@ -96,6 +96,11 @@ def to_numpy(t: torch.Tensor) -> np.ndarray:
 # ------------------------------------------------------------------------------
 # distance matrix
 # ------------------------------------------------------------------------------
+# Longest rows the tensor-core distance is validated for (csrc/prep.cuh kMaxCompensatedDim): beyond
+# it demo_sqdist_f32 uses the fp32 FMA kernel and the fused evaluation the materialised matrix.
+MAX_TENSOR_DIM = 2048
+
+
 def sqdist_device(qf, gf, mode: int = _lib.DIST_SQ, normalize: bool = False, simt: bool = False,
                   want_rowmax: bool = False, want_normalized: bool = False, out: torch.Tensor | None = None):
     """Distance matrix on the device.  Returns ``out`` ([Q, G] fp32 CUDA tensor) or a tuple
@@ -283,6 +288,16 @@ def evaluate_features(qf, gf, q_pids=None, g_pids=None, q_camids=None, g_camids=
     G = g.shape[0]
     if (Q, G) != (plan.Q, plan.G) or g.shape[1] != d:
         raise ValueError("feature / label shapes disagree")
+    if d > MAX_TENSOR_DIM:
+        # outside the validated range of the tensor-core distance: fp32 FMA matrix + streaming count
+        if Q * G > 2 ** 32:
+            raise ValueError("feature dim %d > %d needs the materialised matrix path; %d x %d is too large for it"
+                             % (d, MAX_TENSOR_DIM, Q, G))
+        dist, _, qn, gn = sqdist_device(q, g, normalize=normalize, want_normalized=True)
+        res = evaluate_matrix(dist, plan=plan, max_rank=max_rank)
+        if want_normalized:
+            res.qn, res.gn = qn, gn
+        return res
     max_rank = _effective_max_rank(max_rank, G)
     w = _EvalWorkspace(Q, G, d, plan.T, matrix=False, max_cnt=plan.max_cnt)
     qn = torch.empty((Q, d), dtype=torch.float32, device=q.device) if want_normalized else None

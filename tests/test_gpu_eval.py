@@ -121,6 +121,34 @@ def test_eval_func_edge_cases(M):
     np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
 
 
+@pytest.mark.parametrize("G,nid,levels", [(70000, 350, 0), (9000, 48, 0), (70001, 340, 4096), (3000, 20, 9)])
+def test_eval_func_rows_with_64_to_255_positives(M, G, nid, levels):
+    """Identities with a few hundred gallery images (RGBNT100: ~171 per id): rows with 64 .. 255
+    thresholds go through the arithmetic-bin kernel (count_matrix255_kernel).  Long rows make its
+    private u8 histogram flush several times; quantised distances (levels > 0) tie bit for bit with
+    thresholds, in and across bins; a mis-aligned row start exercises the scalar head."""
+    rng = np.random.default_rng(G + levels)
+    Q = 48
+    dist = rng.standard_normal((Q, G)).astype(np.float32) * 0.05 + 2.0
+    if levels:
+        dist = np.round(dist * levels).astype(np.float32) / np.float32(levels)
+    qp, gp = rng.integers(0, nid, Q), rng.integers(0, nid, G)
+    qc, gc = rng.integers(0, 6, Q), rng.integers(0, 6, G)
+    res = M.evaluate_matrix(dist, qp, gp, qc, gc)
+    ofs, idx, r, c = oracle.rank_counts(dist, qp, gp, qc, gc)
+    per_id = np.bincount(gp, minlength=nid)
+    assert 63 < int(per_id.min()) and int(per_id.max()) <= 255
+    ap_o, first_o = _oracle_per_query(dist, qp, gp, qc, gc)
+    np.testing.assert_array_equal(res.first.cpu().numpy(), first_o)
+    np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
+    ofs2, gidx2, r2, c2 = res.positive_ranks()       # canonical order: gallery index ascending per query
+    np.testing.assert_array_equal(ofs2, ofs)
+    for q in range(Q):
+        o = np.argsort(idx[ofs[q]:ofs[q + 1]], kind="stable")
+        np.testing.assert_array_equal(gidx2[ofs[q]:ofs[q + 1]], idx[ofs[q]:ofs[q + 1]][o])
+        np.testing.assert_array_equal(r2[ofs[q]:ofs[q + 1]], r[ofs[q]:ofs[q + 1]][o])
+
+
 @pytest.mark.parametrize("shape,seed,giq", [("rgbnt201", 0, False), ("rgbnt201", 2, False),
                                             ("rgbnt201", 0, True), ("msvr310", 0, False),
                                             ("rgbnt100", 0, False)])

@@ -61,13 +61,14 @@ for R, C, k in ((10290, 10290, 21), (4096, 262144, 50), (16384, 65536, 21)):
     del m
 
 # rank counts over a materialised matrix (eval_func on a distance matrix): 4 B per pair read once
-for Q, G in ((1715, 8575), (4096, 262144), (8192, 131072)):
+for Q, G, per_id in ((1715, 8575, 20), (4096, 262144, 20), (8192, 131072, 20), (4096, 262144, 170), (1715, 8575, 170)):
     rng = np.random.default_rng(0)
-    nid = max(2, G // 20)
+    nid = max(2, G // per_id)
     qp, gp = rng.integers(0, nid, Q), rng.integers(0, nid, G)
     qc, gc = rng.integers(0, 8, Q), rng.integers(0, 8, G)
     dist = torch.rand(Q, G, device=dev, generator=gen)
     plan = metrics.RankPlan(qp, gp, qc, gc)
     ms = timed(lambda: metrics.evaluate_matrix(dist, plan=plan))
-    report("evaluate_matrix (records+thresholds+count+finalize) %d x %d" % (Q, G), ms, Q * G * 4, "(whole call incl. D2H of the metrics)")
+    report("evaluate_matrix (records+thresholds+count+finalize) %d x %d, ~%d per id" % (Q, G, per_id), ms, Q * G * 4,
+           "(whole call incl. D2H of the metrics)")
     del dist
