@@ -376,7 +376,8 @@ def run_ours(args):
     h2d = (q_host.numel() + g_host.numel()) * 4 + sum(v.numel() * 4 for v in lab_host.values())
     if world > 1 and isinstance(ev.coll, parallel.LibCollectives):
         h2d -= (q_host.numel() - (-(-Q // world)) * d) * 4     # each rank uploads 1/P of the queries; the rest comes over NVLink
-    d2h = 32 + 50 * 4 + (world * (5 * 8) + 8 if world > 1 else 16)  # metrics (mAP | num_valid | cmc) + plan sizes
+    # metrics (mAP | num_valid | cmc) + plan sizes (+ the piece boundaries of the grouped single-GPU path)
+    d2h = 32 + 50 * 4 + (world * (5 * 8) + 8 if world > 1 else 16 + 4 * max(e2e_timers[0].get("query_groups", 1) - 1, 0))
 
     traffic = load_traffic(name, world)
     if rank == 0:
@@ -394,11 +395,14 @@ def run_ours(args):
                         "staged_ms_per_step": staged_ms, "staged_value": Q / (staged_ms * 1e-3),
                         "identical_to_device_resident_result": same,
                         "stage_ms": stage_means(e2e_timers), "slabs": e2e_timers[0].get("slabs"),
+                        "query_groups": e2e_timers[0].get("query_groups", 1),
                         "queried_gallery_rows": e2e_timers[0].get("queried_rows"),
                         "api": "demo2_b200.parallel.ShardedEvaluator.evaluate_host: ONE call per step on pinned host "
                                "features + labels; the prepare kernel pulls the gallery over PCIe (no fp32 copy in HBM), "
-                               "queried rows first, and the count GEMM ranks every slab while the next ones are in flight; "
-                               "cmc/mAP are read back.  staged_* = cudaMemcpy of everything, then the device-resident call."},
+                               "queried rows first (one GPU: per block of pid-sorted queries, so the count GEMM starts after "
+                               "the first block's rows), and the count GEMM ranks every piece while the next ones are in "
+                               "flight; cmc/mAP are read back.  staged_* = cudaMemcpy of everything, then the "
+                               "device-resident call."},
                 "gpu_launches": launches * args.steps,
                 "roofline": {"bound": "tensor",
                              "kernel": "sqdist_gemm2_kernel<EpiCount> (CTA-pair tcgen05 GEMM, fused distance + rank-count)",

@@ -38,8 +38,8 @@ SIGNATURES = {
     "demo_eval_workspace_bytes_ex": (sz, [i32, i32, i32, i64, i32]),
     "demo_eval_matrix_workspace_bytes": (sz, [i32, i32, i64]),
     "demo_eval_prepare": (i32, [vp, i32, i32, i64, i32, i32, i32, i32, vp, sz, i32, i32, i64, vp, sz, vp, vp]),
-    "demo_eval_extract": (i32, [i32, i32, i32, vp, vp, i32, vp, vp, sz, i64, vp, sz, vp, vp, vp, vp]),
-    "demo_eval_count_range": (i32, [i32, i32, i32, i64, vp, sz, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "demo_eval_extract": (i32, [i32, i32, i32, vp, vp, i32, vp, vp, sz, i64, vp, sz, vp, vp, vp, i32, i32, vp]),
+    "demo_eval_count_range": (i32, [i32, i32, i32, i64, vp, sz, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "demo_eval_records": (i32, [vp, vp, i32, i32, i32, i64, i64, i32, vp, vp, i32, vp, sz, i64, vp, sz,
                                 vp, vp, vp, vp, vp, vp]),
     "demo_build_thresholds": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),

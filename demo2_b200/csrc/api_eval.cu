@@ -394,9 +394,12 @@ int demo_eval_prepare(const float* x, int n, int d, int64_t ld, int flags, int w
 // gallery row, used as the tie-break key instead of g_index_base + local row.
 int demo_eval_extract(int Q, int G, int d, const int* q_cam, const int* g_cam, int g_index_base,
                       const int* g_index, const void* plan, size_t plan_bytes, int64_t T, void* ws,
-                      size_t ws_bytes, float* rec_dist, int* rec_gidx, int* rec_junk, void* stream_) {
+                      size_t ws_bytes, float* rec_dist, int* rec_gidx, int* rec_junk, int q_row0, int q_nrows,
+                      void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DEMO_REQUIRE(q_cam && g_cam, "eval_extract: null pointer");
+  DEMO_REQUIRE(q_row0 >= 0 && q_nrows >= 0 && q_row0 + q_nrows <= Q && q_row0 % kBM == 0,
+               "eval_extract: query range [%d, %d) outside [0, %d) or not 128-aligned", q_row0, q_row0 + q_nrows, Q);
   DEMO_REQUIRE(Q > 0 && G > 0 && d > 0, "eval_extract: bad shape");
   PlanView p;
   EvalWs w;
@@ -405,9 +408,11 @@ int demo_eval_extract(int Q, int G, int d, const int* q_cam, const int* g_cam, i
   if (!rec_dist) rec_dist = w.rec_dist;
   if (!rec_gidx) rec_gidx = w.rec_gidx;
   if (!rec_junk) rec_junk = w.rec_junk;
-  gidx_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(p.g_perm, G, g_index_base, g_index, w.b_gidx);
-  DEMO_TRY(launch_fill_records(p, q_cam, g_cam, g_index_base, g_index, rec_gidx, rec_junk, stream));
-  if (T > 0) {
+  if (q_row0 == 0) {   // label-only parts, whole problem: once (the first group of a staged evaluation)
+    gidx_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(p.g_perm, G, g_index_base, g_index, w.b_gidx);
+    DEMO_TRY(launch_fill_records(p, q_cam, g_cam, g_index_base, g_index, rec_gidx, rec_junk, stream));
+  }
+  if (T > 0 && q_nrows > 0) {
     GemmOperands ops;
     DEMO_TRY(make_gemm_operands(w.a, w.b, &ops));
     EpiExtract::Params ep;
@@ -421,7 +426,11 @@ int demo_eval_extract(int Q, int G, int d, const int* q_cam, const int* g_cam, i
     ep.rec_base = p.rec_ofs;
     ep.rec_dist = rec_dist;
     ep.M = Q;
-    const Schedule s = make_list_schedule(Q, G, p.band_list, p.band_count);
+    Schedule s = make_list_schedule(Q, G, p.band_list, p.band_count);
+    if (q_row0 > 0 || q_nrows < Q) {   // one query group: the bands of the other queries are skipped
+      s.m_lo = q_row0;
+      s.m_hi = q_row0 + q_nrows;
+    }
     DEMO_TRY(launch_sqdist_gemm<EpiExtract>(ops, s, p.band_cap, ep, stream));
   }
   return DEMO_OK;
@@ -436,7 +445,7 @@ int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64
   DEMO_TRY(demo_eval_prepare(q, Q, d, ldq, flags, 0, 0, Q, plan, plan_bytes, Q, G, T, ws, ws_bytes, qn_out, stream_));
   DEMO_TRY(demo_eval_prepare(g, G, d, ldg, flags, 1, 0, G, plan, plan_bytes, Q, G, T, ws, ws_bytes, gn_out, stream_));
   return demo_eval_extract(Q, G, d, q_cam, g_cam, g_index_base, nullptr, plan, plan_bytes, T, ws, ws_bytes, rec_dist,
-                           rec_gidx, rec_junk, stream_);
+                           rec_gidx, rec_junk, 0, Q, stream_);
 }
 
 int demo_build_thresholds(const int* rec_ofs, const float* rec_dist, const int* rec_gidx, const int* rec_junk,
@@ -452,11 +461,25 @@ int demo_build_thresholds(const int* rec_ofs, const float* rec_dist, const int* 
 // path when the workspace was sized with demo_eval_workspace_bytes_ex(.., max_cnt).
 int demo_eval_count_range(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes, const int* thr_ofs,
                           const int* thr_cnt, const float* thr_val, const int* thr_gidx, unsigned* counts,
-                          int max_cnt, int chunk_tiles, int g_row0, int g_nrows, int reserve_sms, void* stream_) {
+                          int max_cnt, int chunk_tiles, int g_row0, int g_nrows, int q_row0, int q_nrows,
+                          int reserve_sms, void* stream_) {
   EvalWs w;
   DEMO_REQUIRE(g_row0 >= 0 && g_nrows >= 0 && g_row0 + g_nrows <= G, "eval_count: gallery range outside [0, %d)", G);
+  DEMO_REQUIRE(q_row0 >= 0 && q_nrows >= 0 && q_row0 + q_nrows <= Q, "eval_count: query range outside [0, %d)", Q);
   DEMO_TRY(get_ws(ws, ws_bytes, Q, G, d, T_local, &w, max_cnt));
-  return count_features(w, Q, g_row0, g_nrows, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, chunk_tiles,
+  if (q_nrows == 0) return DEMO_OK;
+  if (q_row0 > 0 || q_nrows < Q) {
+    // a block of pid-sorted queries: the same launch on a shifted view (thr_ofs holds absolute offsets)
+    const int align = w.slab != nullptr && max_cnt > kWin ? w.slab_rows : 2 * kBM;
+    DEMO_REQUIRE(q_row0 % align == 0, "eval_count: query range must start at a multiple of %d rows", align);
+    w.a = sub_rows(w.a, q_row0, q_nrows);
+    w.blk_flag += q_row0 >> 8;
+    w.blk_unflag += q_row0 >> 8;
+    w.slab_any += q_row0 / w.slab_rows;
+    thr_ofs += q_row0;
+    thr_cnt += q_row0;
+  }
+  return count_features(w, q_nrows, g_row0, g_nrows, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, chunk_tiles,
                         static_cast<cudaStream_t>(stream_), reserve_sms);
 }
 
@@ -464,7 +487,7 @@ int demo_eval_count(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_by
                     const int* thr_cnt, const float* thr_val, const int* thr_gidx, unsigned* counts,
                     int max_cnt, int chunk_tiles, void* stream_) {
   return demo_eval_count_range(Q, G, d, T_local, ws, ws_bytes, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt,
-                               chunk_tiles, 0, G, 0, stream_);
+                               chunk_tiles, 0, G, 0, Q, 0, stream_);
 }
 
 int demo_cmc_map_finalize(const int* thr_ofs, const int* thr_cnt, const int* thr_junk, const unsigned* counts,

@@ -64,6 +64,8 @@ struct Schedule {
   // Optional per-256-row-block flags (device): units of a flagged A block are empty for this launch
   // (the fused rank count leaves query blocks with more thresholds than one window to the slab path).
   const unsigned char* m_skip = nullptr;
+  // Units whose A block starts outside [m_lo, m_hi) are empty (extract pass of one query group).
+  int m_lo = 0, m_hi = 0x7fffffff;
   // Symmetric all-pairs problems (A and B are row ranges of one set with global offsets tri_a0 /
   // tri_b0): tiles that hold no element with (global row) <= (global column) are empty.
   int tri = 0, tri_a0 = 0, tri_b0 = 0;
@@ -107,6 +109,7 @@ __device__ __forceinline__ WorkUnit schedule_get(const Schedule& s, int u) {
     w.n_rows = e.z;
   }
   if (s.m_skip != nullptr && __ldg(s.m_skip + (w.m0 >> 8)) != 0) w.n_rows = 0;
+  if (w.m0 < s.m_lo || w.m0 >= s.m_hi) w.n_rows = 0;
   if (s.tri && s.tri_a0 + w.m0 > s.tri_b0 + w.n0 + w.n_rows - 1) w.n_rows = 0;
   return w;
 }

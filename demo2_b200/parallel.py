@@ -190,10 +190,11 @@ class CudaEngine:
                                          int(nrows), ptr(plan.buf), plan.nbytes, plan.Q, plan.G, plan.T, ptr(w.buf),
                                          w.nbytes, None, stream_ptr()))
 
-    def extract(self, plan, w, g_index_base, g_index=None):
+    def extract(self, plan, w, g_index_base, g_index=None, q_row0=0, q_nrows=None):
+        q_nrows = plan.Q - q_row0 if q_nrows is None else q_nrows
         check(self.lib.demo_eval_extract(plan.Q, plan.G, w.d, ptr(plan.q_cam), ptr(plan.g_cam), int(g_index_base),
                                          ptr(g_index), ptr(plan.buf), plan.nbytes, plan.T, ptr(w.buf), w.nbytes,
-                                         None, None, None, stream_ptr()))
+                                         None, None, None, int(q_row0), int(q_nrows), stream_ptr()))
         n = max(plan.T, 1)
         recs = torch.stack([w.view("rec_dist", torch.float32, n).view(torch.int32),
                             w.view("rec_gidx", torch.int32, n), w.view("rec_junk", torch.int32, n)])
@@ -220,12 +221,26 @@ class CudaEngine:
                                              ptr(thr_cnt), ptr(thr_val), ptr(thr_gidx), ptr(thr_junk), stream_ptr()))
         return thr_cnt, thr_val, thr_gidx, thr_junk
 
+    def thresholds_alloc(self, T, Q, dev):
+        n = max(int(T), 1)
+        return (torch.empty(Q, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float32, device=dev),
+                torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev))
+
+    def thresholds_into(self, rec_ofs, recs, thr, q_row0, q_nrows):
+        """Thresholds of the pid-sorted queries [q_row0, q_row0 + q_nrows) into preallocated arrays
+        (rec_ofs holds absolute offsets, so a query block is a shifted view)."""
+        thr_cnt, thr_val, thr_gidx, thr_junk = thr
+        check(self.lib.demo_build_thresholds(ptr(rec_ofs[q_row0:]), ptr(recs[0]), ptr(recs[1]), ptr(recs[2]),
+                                             int(q_nrows), ptr(thr_cnt[q_row0:]), ptr(thr_val), ptr(thr_gidx),
+                                             ptr(thr_junk), stream_ptr()))
+
     def count(self, w, plan, thr_ofs, thr_cnt, thr_val, thr_gidx, counts, max_cnt, g_row0=0, g_nrows=None,
-              reserve_sms=0):
+              reserve_sms=0, q_row0=0, q_nrows=None):
         g_nrows = w.G - g_row0 if g_nrows is None else g_nrows
+        q_nrows = w.Q - q_row0 if q_nrows is None else q_nrows
         check(self.lib.demo_eval_count_range(w.Q, w.G, w.d, plan.T, ptr(w.buf), w.nbytes, ptr(thr_ofs), ptr(thr_cnt),
                                              ptr(thr_val), ptr(thr_gidx), ptr(counts), int(max_cnt), 0, int(g_row0),
-                                             int(g_nrows), int(reserve_sms), stream_ptr()))
+                                             int(g_nrows), int(q_row0), int(q_nrows), int(reserve_sms), stream_ptr()))
 
     def finalize(self, thr_ofs, thr_cnt, thr_junk, counts, q_perm, Q, max_rank):
         dev = counts.device
@@ -378,7 +393,8 @@ class ShardedEvaluator:
     # ---- host-resident inputs: the gallery is pulled in slab by slab while the GEMM ranks --------
     def evaluate_host(self, q_host, g_host_local, q_pid, g_pid_local, q_cam, g_cam_local, g_index_base: int = 0,
                       normalize: bool = False, max_rank: int = 50, timers: dict | None = None,
-                      slab_rows: int = 131072, shard_query_upload: bool = True, reserve_sms: int | None = None):
+                      slab_rows: int = 131072, shard_query_upload: bool = True, reserve_sms: int | None = None,
+                      query_groups: int | None = None):
         """One evaluation whose features live in PINNED HOST memory (what R1_mAP_eval.update
         accumulates when the model runs elsewhere, utils/metrics.py:244).  No fp32 copy of the
         gallery is made on the device: demo_eval_prepare pulls the rows over PCIe in pid-sorted
@@ -391,6 +407,14 @@ class ShardedEvaluator:
         assert isinstance(eng, CudaEngine), "evaluate_host needs the CUDA engine"
         if reserve_sms is None:
             reserve_sms = int(os.environ.get("DEMO_RESERVE_SMS", "0"))   # env: experiments
+        if query_groups is None:
+            query_groups = int(os.environ.get("DEMO_QUERY_GROUPS", "4"))
+        if (self.world == 1 and query_groups > 1 and len(g_pid_local) > 0 and q_host.shape[0] >= 2 * 1024
+                and isinstance(g_host_local, torch.Tensor) and not g_host_local.is_cuda and g_host_local.is_pinned()
+                and g_host_local.dtype == torch.float32 and g_host_local.dim() == 2 and g_host_local.stride(1) == 1
+                and g_host_local.shape[1] % 4 == 0 and g_host_local.shape[1] <= 2048):
+            return self._evaluate_host_grouped(q_host, g_host_local, q_pid, g_pid_local, q_cam, g_cam_local,
+                                               g_index_base, normalize, max_rank, timers, slab_rows, query_groups)
         dev = torch.device("cuda", torch.cuda.current_device())
         ev = eng.event if timers is not None else None
         mark = (lambda: ev()) if ev else (lambda: None)
@@ -480,6 +504,102 @@ class ShardedEvaluator:
                 + max(len(bounds) - 3, 0)
             timers["slabs"] = len(bounds) - 1
             timers["queried_rows"] = plan.n_queried
+        return res
+
+    def _evaluate_host_grouped(self, q_host, g_host, q_pid, g_pid, q_cam, g_cam, g_index_base, normalize, max_rank,
+                               timers, slab_rows, groups):
+        """evaluate_host on one GPU with the ranking started before the queried gallery rows are
+        all in: the pid-sorted queries are cut into `groups` blocks; the gallery rows block j asks
+        for are a contiguous piece of the sorted gallery, pulled over PCIe in that order by the side
+        stream (one continuous transfer: pieces 0 .. groups-1, then the rest in slabs).  As soon
+        as piece j has landed the main stream extracts the records of block j, builds its
+        thresholds and counts the two new rectangles (blocks 0..j x piece j, block j x pieces
+        0..j-1) -- rank counts are additive over any tiling of Q x G -- so the tensor cores start
+        after 1 / groups of the first phase instead of after all of it."""
+        eng = self.engine
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ev = eng.event if timers is not None else None
+        mark = (lambda: ev()) if ev else (lambda: None)
+        t0 = mark()
+        plan = eng.plan(q_pid, g_pid, q_cam, g_cam)
+        Q, G, d = plan.Q, plan.G, q_host.shape[1]
+        K = max(1, min(int(groups), Q // 1024))
+        qb = [0] + [min(Q, -(-(j * Q) // (K * 1024)) * 1024) for j in range(1, K)] + [Q]
+        qb = sorted(set(qb))
+        K = len(qb) - 1
+        # gallery rows the queries before each boundary ask for: end of the band of the last such query
+        last = torch.tensor([b - 1 for b in qb[1:]], dtype=torch.int64, device=plan.g_lo.device)
+        ends = plan.g_lo[last] + plan.rec_ofs[last + 1] - plan.rec_ofs[last]
+        host = torch.cat([plan.info, ends.to(torch.int32)]).cpu()          # the one host round trip
+        plan.finish(host[:4])
+        T, max_cnt = plan.T, plan.max_cnt
+        p0 = min(G, -(-max(plan.n_queried, 1) // 256) * 256)
+        gb = [0] + [min(p0, int(e)) for e in host[4:4 + K - 1].tolist()] + [p0]
+        for j in range(1, len(gb)):
+            gb[j] = max(gb[j], gb[j - 1])
+        bounds = [p0]
+        while bounds[-1] < G:
+            bounds.append(min(G, bounds[-1] + slab_rows))
+        t1 = mark()
+        main = torch.cuda.current_stream()
+        w = eng.workspace(plan, d, max_cnt)
+        pinned_q = (isinstance(q_host, torch.Tensor) and not q_host.is_cuda and q_host.is_pinned()
+                    and q_host.dtype == torch.float32 and q_host.dim() == 2 and q_host.stride(1) == 1)
+        if pinned_q:
+            eng.prepare(plan, w, q_host, 0, 0, Q, normalize, host_input=True)
+        else:
+            from .metrics import _features
+            eng.prepare(plan, w, _features(q_host), 0, 0, Q, normalize)
+        start = torch.cuda.Event()
+        start.record(main)
+        side = self._side_stream()
+        side.wait_event(start)
+        piece_in, slab_in = [], []
+        with torch.cuda.stream(side):
+            for j in range(K):
+                eng.prepare(plan, w, g_host, 1, gb[j], gb[j + 1] - gb[j], normalize, host_input=True)
+                e = torch.cuda.Event()
+                e.record(side)
+                piece_in.append(e)
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                eng.prepare(plan, w, g_host, 1, a, b - a, normalize, host_input=True)
+                e = torch.cuda.Event()
+                e.record(side)
+                slab_in.append(e)
+        thr = eng.thresholds_alloc(T, Q, dev)
+        counts = torch.zeros(max(T, 1), dtype=torch.int32, device=dev)
+        recs = None
+        n_count = 0
+        for j in range(K):
+            main.wait_event(piece_in[j])
+            recs = eng.extract(plan, w, g_index_base, q_row0=qb[j], q_nrows=qb[j + 1] - qb[j])
+            if T > 0:
+                eng.thresholds_into(plan.rec_ofs, recs, thr, qb[j], qb[j + 1] - qb[j])
+                if gb[j + 1] > gb[j]:      # every block known so far x the new piece
+                    eng.count(w, plan, plan.rec_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=gb[j],
+                              g_nrows=gb[j + 1] - gb[j], q_row0=0, q_nrows=qb[j + 1])
+                    n_count += 1
+                if j > 0 and gb[j] > 0:    # the new block x the pieces that were already there
+                    eng.count(w, plan, plan.rec_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=0, g_nrows=gb[j],
+                              q_row0=qb[j], q_nrows=qb[j + 1] - qb[j])
+                    n_count += 1
+        t2 = mark()
+        for i, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+            main.wait_event(slab_in[i])
+            if T > 0 and b > a:
+                eng.count(w, plan, plan.rec_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=a, g_nrows=b - a)
+                n_count += 1
+        t3 = mark()
+        res = self._finish(plan, thr, counts, plan.rec_ofs, G, max_rank)
+        t4 = mark()
+        if timers is not None and ev:
+            timers.update({"plan": (t0, t1), "queried pieces: upload + records + thresholds + count": (t1, t2),
+                           "count(+upload of the other slabs)": (t2, t3), "finalize": (t3, t4)})
+            timers["launches"] = eng.launches(max(n_count, 1), (-(-Q // 256) if max_cnt > 63 else 0) * max(n_count, 1)) \
+                + K + len(bounds) - 1 + 2 * (K - 1)
+            timers["slabs"] = K + len(bounds) - 1
+            timers["queried_rows"] = plan.n_queried
+            timers["query_groups"] = K
         return res
 
     def _side_stream(self):

@@ -107,7 +107,14 @@ DEMO_API size_t demo_eval_matrix_workspace_bytes(int Q, int G, int64_t T);
  *                         itself, in sorted order (queried rows first), slab by slab.
  *   demo_eval_extract     records from the prepared queries + queried gallery rows; g_index
  *                         (optional, [G]) = global gallery index per local row (tie-break key).
- *   demo_eval_count_range counts against the sorted gallery rows [g_row0, g_row0+g_nrows);
+ *                         [q_row0, q_row0+q_nrows) (pid-sorted queries, 128-aligned start; 0, Q =
+ *                         all): only the records of that query group -- its gallery rows (a prefix
+ *                         of the sorted gallery) must be prepared, the later ones may still be in
+ *                         flight.
+ *   demo_eval_count_range counts the pid-sorted queries [q_row0, q_row0+q_nrows) (start a multiple
+ *                         of 256 rows, 1024 with the slab path) against the sorted gallery rows
+ *                         [g_row0, g_row0+g_nrows): the (query block x gallery block) rectangles of
+ *                         successive calls must tile Q x G exactly once;
  *                         reserve_sms > 0: the persistent GEMM grid leaves that many SMs free for
  *                         the kernel that pulls in the next slab meanwhile.                      */
 DEMO_API int demo_eval_prepare(const float* x, int n, int d, int64_t ld, int flags, int which, int row0, int nrows,
@@ -115,11 +122,13 @@ DEMO_API int demo_eval_prepare(const float* x, int n, int d, int64_t ld, int fla
                                size_t ws_bytes, float* xn_out, void* stream);
 DEMO_API int demo_eval_extract(int Q, int G, int d, const int* q_cam, const int* g_cam, int g_index_base,
                                const int* g_index, const void* plan, size_t plan_bytes, int64_t T, void* ws,
-                               size_t ws_bytes, float* rec_dist, int* rec_gidx, int* rec_junk, void* stream);
+                               size_t ws_bytes, float* rec_dist, int* rec_gidx, int* rec_junk, int q_row0,
+                               int q_nrows, void* stream);
 DEMO_API int demo_eval_count_range(int Q, int G, int d, int64_t T_local, void* ws, size_t ws_bytes,
                                    const int* thr_ofs, const int* thr_cnt, const float* thr_val,
                                    const int* thr_gidx, unsigned* counts, int max_cnt, int chunk_tiles,
-                                   int g_row0, int g_nrows, int reserve_sms, void* stream);
+                                   int g_row0, int g_nrows, int q_row0, int q_nrows, int reserve_sms,
+                                   void* stream);
 DEMO_API int demo_eval_records(const float* q, const float* g, int Q, int G, int d, int64_t ldq, int64_t ldg,
                                int flags, const int* q_cam, const int* g_cam, int g_index_base,
                                const void* plan, size_t plan_bytes, int64_t T, void* ws, size_t ws_bytes,

@@ -158,6 +158,38 @@ def test_streamed_host_evaluation_equals_device_evaluation(slab_rows):
     assert float(res2.mAP) == float(single.mAP)
 
 
+@pytest.mark.parametrize("Q,G,nid,groups", [(2600, 12000, 400, 4), (4200, 9000, 700, 3), (2100, 8000, 30, 2)])
+def test_streamed_host_evaluation_query_groups(Q, G, nid, groups):
+    """One GPU, >= 2048 queries: the queried gallery rows are pulled in per block of pid-sorted
+    queries and the count GEMM starts on the first block's rectangle while the others are still in
+    flight (ShardedEvaluator._evaluate_host_grouped).  The rectangles tile Q x G exactly once:
+    same integers as the device-resident evaluation (nid = 30: ~270 gallery images per id, slab path)."""
+    from demo2_b200 import metrics, parallel
+    rng = np.random.default_rng(Q + G)
+    d = 128
+    centers = rng.standard_normal((nid, d)).astype(np.float32)
+    qp, gp = rng.integers(0, nid, Q), rng.integers(0, nid, G)
+    gp[::4] += 5000                              # a quarter of the gallery has ids no query asks for
+    qp[:7] = 77777                               # and a few queries ask for an id the gallery lacks
+    qc, gc = rng.integers(0, 4, Q), rng.integers(0, 4, G)
+    qf = centers[qp % nid] + 2.0 * rng.standard_normal((Q, d)).astype(np.float32)
+    gf = centers[gp % nid] + 2.0 * rng.standard_normal((G, d)).astype(np.float32)
+    gf[::13] = qf[rng.integers(0, Q, len(gf[::13]))]        # exact duplicates: ties
+    single = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, normalize=True)
+    ev = parallel.ShardedEvaluator()
+    timers = {}
+    res = ev.evaluate_host(torch.from_numpy(qf).pin_memory(), torch.from_numpy(gf).pin_memory(), qp, gp, qc, gc,
+                           normalize=True, slab_rows=2048, timers=timers, query_groups=groups)
+    assert timers["query_groups"] >= 2
+    np.testing.assert_array_equal(res.cmc, single.cmc)
+    assert float(res.mAP) == float(single.mAP)
+    np.testing.assert_array_equal(res.ap.cpu().numpy(), single.ap.cpu().numpy())
+    np.testing.assert_array_equal(res.first.cpu().numpy(), single.first.cpu().numpy())
+    r1, r2 = res.positive_ranks(), single.positive_ranks()
+    for a, b in zip(r1, r2):
+        np.testing.assert_array_equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------
 # more thresholds than one window: slab path
 # ---------------------------------------------------------------------------------------------
