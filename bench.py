@@ -497,9 +497,18 @@ def other_workloads(dev, peaks, with_cpu=True):
     from demo2_b200 import metrics, reranking, synth, triplet_loss
     from oracle import reid_oracle as oracle
 
-    def timed(fn, iters=10, warm=3):
-        for _ in range(warm):
+    def timed(fn, iters=10, warm=3, busy_s=0.2):
+        # warm-up: at least `warm` calls AND `busy_s` of continuous GPU work -- these workloads take
+        # a millisecond or less, and after the CPU legs (seconds of host-only work) the GPU needs
+        # tens of milliseconds to leave its idle clocks (measured: the first 10 calls after a CPU
+        # leg ran 8-15x slower than the same calls a moment later)
+        t0 = time.perf_counter()
+        n = 0
+        while n < warm or time.perf_counter() - t0 < busy_s:
             fn()
+            n += 1
+            if n % 4 == 0:
+                torch.cuda.synchronize()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -599,6 +608,45 @@ def other_workloads(dev, peaks, with_cpu=True):
             return tot
         trip["batched_fwd_ms"], _ = timed(fwd_multi, iters=50)
         trip["batched_fwd_bwd_ms"], _ = timed(fwd_bwd_multi, iters=50)
+        # the same forward + backward captured in a CUDA graph (what a captured training step pays: the
+        # two kernels, no Python / autograd dispatch); check=False: no status copy inside the capture
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+
+            def fb_nocheck():
+                tot = triplet_loss.triplet_loss_multi(xs, labels, check=False)[0].sum()
+                tot.backward()
+                return tot
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    for x in xs:
+                        x.grad = None
+                    fb_nocheck()
+            torch.cuda.current_stream().wait_stream(side)
+            for x in xs:
+                x.grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = fb_nocheck()
+            graph.replay()
+            torch.cuda.synchronize()
+            eager = triplet_loss.triplet_loss_multi(xs, labels, check=False)[0].sum()
+            trip["graphed_fwd_bwd_ms"], _ = timed(graph.replay, iters=200)
+            trip["graphed_matches_eager"] = bool(torch.equal(static_loss.detach(), eager.detach()))
+
+            def f_nocheck():
+                with torch.no_grad():
+                    return triplet_loss.triplet_loss_multi(xs, labels, check=False)[0]
+            gf = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                f_nocheck()
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.cuda.graph(gf):
+                f_nocheck()
+            trip["graphed_fwd_ms"], _ = timed(gf.replay, iters=200)
+        except Exception as exc:  # a capture problem must not cost the headline line
+            trip["graphed_error"] = repr(exc)
     # the reference's own algorithm (layers/triplet_loss.py:16-31, 51-104, 121-135) in eager torch on this GPU
     ref_f, ref_fb = torch_eager_triplet(xs, labels, timed)
     trip["torch_eager_reference_algorithm"] = {"fwd_ms": ref_f, "fwd_bwd_ms": ref_fb,

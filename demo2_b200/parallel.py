@@ -27,6 +27,26 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 
+_NVTX = bool(os.environ.get("DEMO_NVTX"))
+
+
+class _Phases:
+    """NVTX ranges around the stages of an evaluation (DEMO_NVTX=1; for nsys timelines of the
+    multi-GPU step: plan / records / exchange / thresholds / count / allreduce / finalize)."""
+
+    def __init__(self):
+        self.open = False
+
+    def __call__(self, name=None):
+        if not _NVTX:
+            return
+        if self.open:
+            torch.cuda.nvtx.range_pop()
+        if name:
+            torch.cuda.nvtx.range_push("demo:" + name)
+        self.open = bool(name)
+
+
 def shard_range(G: int, world: int, rank: int):
     """Contiguous gallery shard [lo, hi) of `rank`."""
     base, rem = divmod(G, world)
@@ -355,11 +375,14 @@ class ShardedEvaluator:
         eng = self.engine
         ev = getattr(eng, "event", None) if timers is not None else None
         mark = (lambda: ev()) if ev else (lambda: None)
+        ph = _Phases()
 
         t0 = mark()
+        ph("plan")
         plan, n_local, sizes = self._plan_and_sizes(q_pid, g_pid_local, q_cam, g_cam_local)
         Q = plan.Q
         t1 = mark()
+        ph("records")
         max_all = sizes["max_all"] if sizes else plan.max_cnt
         if n_local > 0:
             kw = {}
@@ -371,19 +394,25 @@ class ShardedEvaluator:
         else:
             w, recs = None, torch.zeros((3, 0), dtype=torch.int32, device=plan.rec_ofs.device)
         t2 = mark()
+        ph("exchange")
         thr_ofs, merged, T, max_cnt = self._exchange(plan, recs, sizes)
         t3 = mark()
+        ph("thresholds")
         thr = eng.thresholds(thr_ofs, merged, Q)
         counts = torch.zeros(max(T, 1), dtype=torch.int32, device=merged.device)
         t4 = mark()
+        ph("count")
         if T > 0 and n_local > 0:
             eng.count(w, plan, thr_ofs, thr[0], thr[1], thr[2], counts, max_cnt)
         t5 = mark()
+        ph("allreduce")
         if self.world > 1:
             self.coll.all_reduce_sum(counts)
         t6 = mark()
+        ph("finalize")
         res = self._finish(plan, thr, counts, thr_ofs, sizes["G_total"] if sizes else n_local, max_rank)
         t7 = mark()
+        ph()
         if timers is not None and ev:
             timers.update({"plan": (t0, t1), "records": (t1, t2), "exchange": (t2, t3), "thresholds": (t3, t4),
                            "count": (t4, t5), "allreduce": (t5, t6), "finalize": (t6, t7)})

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 DIST_RTOL, DIST_ATOL = 1e-5, 2e-6   # BASELINE.json: 1e-5 relative (+ absolute floor for ~0 entries)
 # Against the REFERENCE's metrics (another fp32 GEMM: MKL there, tcgen05 here).  Measured on B200
-# over the six golden cases (profiles/parity_r2.txt): CMC identical, first-match rank identical for
+# over the six golden cases (profiles/parity_r2.jsonl): CMC identical, first-match rank identical for
 # every query, |dmAP| <= 3.1e-6 (5 near-tied positives of one case swap places; on the queries
 # without near-ties the ranks are EXACT, test_rank_indices_exact_outside_near_ties).
 XGEMM_METRIC_ATOL = 5e-6
@@ -305,11 +305,12 @@ def test_fused_eval_small_and_ragged_shapes(M, Q, G, d):
     np.testing.assert_allclose(res.ap.cpu().numpy(), ap_o, atol=1e-12)
 
 
-@pytest.mark.parametrize("d", [64, 768, 1536, 2048])
+@pytest.mark.parametrize("d", [64, 768, 1536, 2048, 4096])
 def test_near_duplicate_distances_are_bias_compensated(M, d):
     """The tensor cores accumulate with round-toward-zero; un-compensated, exact duplicates of unit
     rows came out at 1.9e-5 (d = 1536) instead of 0.  prep.cu folds the calibrated mean bias into the
-    row scales: duplicates and high-cosine pairs stay within 1e-5 absolute of the fp64 result."""
+    row scales: duplicates and high-cosine pairs stay within 1e-5 absolute of the fp64 result.  Rows
+    longer than the validated range (d > 2048) take the fp32 FMA kernel: same bound."""
     rng = np.random.default_rng(d)
     a = oracle.l2_normalize(rng.standard_normal((200, d)).astype(np.float32))
     noise = oracle.l2_normalize(rng.standard_normal((200, d)).astype(np.float32))
