@@ -422,7 +422,7 @@ class ShardedEvaluator:
     # ---- host-resident inputs: the gallery is pulled in slab by slab while the GEMM ranks --------
     def evaluate_host(self, q_host, g_host_local, q_pid, g_pid_local, q_cam, g_cam_local, g_index_base: int = 0,
                       normalize: bool = False, max_rank: int = 50, timers: dict | None = None,
-                      slab_rows: int = 131072, shard_query_upload: bool = True, reserve_sms: int | None = None,
+                      slab_rows: int | None = None, shard_query_upload: bool = True, reserve_sms: int | None = None,
                       query_groups: int | None = None):
         """One evaluation whose features live in PINNED HOST memory (what R1_mAP_eval.update
         accumulates when the model runs elsewhere, utils/metrics.py:244).  No fp32 copy of the
@@ -482,8 +482,9 @@ class ShardedEvaluator:
         G = plan.G
         p0 = min(G, -(-max(plan.n_queried, 1) // 256) * 256) if n_local > 0 else 0
         bounds = [0, p0]
+        step = self._slab_rows(slab_rows, G - p0)
         while bounds[-1] < G and n_local > 0:
-            bounds.append(min(G, bounds[-1] + slab_rows))
+            bounds.append(min(G, bounds[-1] + step))
         up_events = []
         if n_local > 0:
             eng.prepare(plan, w, g_src, 1, 0, p0, normalize, host_input=g_host_in)
@@ -567,8 +568,9 @@ class ShardedEvaluator:
         for j in range(1, len(gb)):
             gb[j] = max(gb[j], gb[j - 1])
         bounds = [p0]
+        step = self._slab_rows(slab_rows, G - p0)
         while bounds[-1] < G:
-            bounds.append(min(G, bounds[-1] + slab_rows))
+            bounds.append(min(G, bounds[-1] + step))
         t1 = mark()
         main = torch.cuda.current_stream()
         w = eng.workspace(plan, d, max_cnt)
@@ -630,6 +632,16 @@ class ShardedEvaluator:
             timers["queried_rows"] = plan.n_queried
             timers["query_groups"] = K
         return res
+
+    @staticmethod
+    def _slab_rows(slab_rows, rest):
+        """Rows per slab of the gallery part that is pulled in behind the queried rows.  A slab is
+        counted only once it has landed completely, so with a small shard (8 ranks: 84k rows, where
+        the step is bound by the 8 concurrent PCIe streams, ~22 GB/s each) ONE 131 072-row slab left
+        the tensor cores waiting for the whole transfer: at least six slabs, 8 192 .. 131 072 rows."""
+        if slab_rows is not None:
+            return max(1, int(slab_rows))
+        return max(8192, min(131072, -(-rest // (6 * 256)) * 256))
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
