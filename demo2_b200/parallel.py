@@ -307,7 +307,19 @@ class ShardedEvaluator:
         self.coll = collectives
 
     # ---- label-only part: plan, [sizes of every rank], one host read ---------------------------
-    def _plan_and_sizes(self, q_pid, g_pid_local, q_cam, g_cam_local):
+    @staticmethod
+    def _query_bounds(Q, groups):
+        """Boundaries of the pid-sorted query blocks of the grouped streamed evaluation (multiples of
+        1024 rows: the slab granularity of the count path)."""
+        K = max(1, min(int(groups), Q // 1024))
+        qb = [0] + [min(Q, -(-(j * Q) // (K * 1024)) * 1024) for j in range(1, K)] + [Q]
+        return sorted(set(qb))
+
+    def _plan_and_sizes(self, q_pid, g_pid_local, q_cam, g_cam_local, groups=None, local_ok=True):
+        """groups (several ranks, streamed evaluation): also returns, from the same host read, what the
+        grouped flow needs per query block -- local record offsets, the end of the local gallery piece
+        the block asks for, the longest per-rank record slice and the global record offset -- and
+        whether EVERY rank can take that flow (sizes["groups"]["ok"])."""
         eng = self.engine
         n_local = int(len(g_pid_local))
         if n_local == 0:
@@ -326,17 +338,36 @@ class ShardedEvaluator:
         sizes = None
         if self.world > 1:
             cnt_local = (plan.rec_ofs[1:] - plan.rec_ofs[:-1]).to(torch.int32)
+            tail = [n_local] + ([1 if (local_ok and n_local > 0) else 0] if groups else [])
             meta = torch.cat([cnt_local, info.to(torch.int32),
-                              torch.tensor([n_local], dtype=torch.int32, device=cnt_local.device)])
-            gathered = self.coll.all_gather(meta)                                   # [P, Q + 5]
+                              torch.tensor(tail, dtype=torch.int32, device=cnt_local.device)])
+            gathered = self.coll.all_gather(meta)                                   # [P, Q + 5 (+ 1)]
             cnt_all = gathered[:, :Q]
             tot_max = cnt_all.sum(0).max().reshape(1).to(torch.int64) if Q else torch.zeros(1, dtype=torch.int64)
-            host = torch.cat([gathered[:, Q:].reshape(-1).to(torch.int64), tot_max.to(gathered.device)]).cpu()
-            per_rank = host[:-1].reshape(self.world, 5)
+            P, W = self.world, 5 + (1 if groups else 0)
+            extra, qb = [], None
+            if groups:
+                qb = self._query_bounds(Q, groups)
+                K = len(qb) - 1
+                idx = torch.tensor(qb, dtype=torch.int64, device=gathered.device)
+                last = idx[1:] - 1
+                rec_ofs = plan.rec_ofs.to(gathered.device)
+                ends = plan.g_lo.to(gathered.device)[last] + rec_ofs[last + 1] - rec_ofs[last]
+                pre = torch.zeros((P, Q + 1), dtype=torch.int64, device=gathered.device)
+                pre[:, 1:] = torch.cumsum(cnt_all.to(torch.int64), 1)
+                at = pre[:, idx]                                                    # [P, K + 1]
+                extra = [rec_ofs[idx].to(torch.int64), ends.to(torch.int64),
+                         (at[:, 1:] - at[:, :-1]).max(0).values, at.sum(0)]
+            host = torch.cat([gathered[:, Q:].reshape(-1).to(torch.int64), tot_max.to(gathered.device)] + extra).cpu()
+            per_rank = host[:P * W].reshape(P, W)
             if deferred:
                 plan.finish(per_rank[self.rank, :4])
             sizes = dict(cnt_all=cnt_all, t_max=int(per_rank[:, 0].max()), T_sum=int(per_rank[:, 0].sum()),
-                         G_total=int(per_rank[:, 4].sum()), max_all=int(host[-1]))
+                         G_total=int(per_rank[:, 4].sum()), max_all=int(host[P * W]))
+            if groups:
+                x = host[P * W + 1:].tolist()
+                sizes["groups"] = dict(qb=qb, rec_lo=x[:K + 1], ends=x[K + 1:2 * K + 1], gmax=x[2 * K + 1:3 * K + 1],
+                                       gofs=x[3 * K + 1:4 * K + 2], ok=bool(per_rank[:, 5].min() > 0) and K > 1)
         elif deferred:
             plan.finish(info.cpu())
         return plan, n_local, sizes
@@ -451,7 +482,9 @@ class ShardedEvaluator:
             and t.dim() == 2 and t.stride(1) == 1 and t.shape[1] % 4 == 0 and t.shape[1] <= 2048
 
         t0 = mark()
-        plan, n_local, sizes = self._plan_and_sizes(q_pid, g_pid_local, q_cam, g_cam_local)
+        want_groups = query_groups if (self.world > 1 and query_groups > 1 and q_host.shape[0] >= 2 * 1024) else None
+        plan, n_local, sizes = self._plan_and_sizes(q_pid, g_pid_local, q_cam, g_cam_local, groups=want_groups,
+                                                    local_ok=pinned(g_host_local))
         Q = plan.Q
         max_all = sizes["max_all"] if sizes else plan.max_cnt
         t1 = mark()
@@ -474,6 +507,9 @@ class ShardedEvaluator:
             else:
                 from .metrics import _features
                 eng.prepare(plan, w, _features(q_host), 0, 0, Q, normalize)
+        if sizes and sizes.get("groups") and sizes["groups"]["ok"]:
+            return self._host_grouped_ranks(plan, sizes, w, g_host_local, g_index_base, normalize, max_rank, timers,
+                                            slab_rows, (t0, t1))
         # -- gallery slab 0: the queried rows
         g_src, g_host_in = g_host_local, pinned(g_host_local)
         if n_local > 0 and not g_host_in:
@@ -553,9 +589,7 @@ class ShardedEvaluator:
         t0 = mark()
         plan = eng.plan(q_pid, g_pid, q_cam, g_cam)
         Q, G, d = plan.Q, plan.G, q_host.shape[1]
-        K = max(1, min(int(groups), Q // 1024))
-        qb = [0] + [min(Q, -(-(j * Q) // (K * 1024)) * 1024) for j in range(1, K)] + [Q]
-        qb = sorted(set(qb))
+        qb = self._query_bounds(Q, groups)
         K = len(qb) - 1
         # gallery rows the queries before each boundary ask for: end of the band of the last such query
         last = torch.tensor([b - 1 for b in qb[1:]], dtype=torch.int64, device=plan.g_lo.device)
@@ -626,6 +660,98 @@ class ShardedEvaluator:
         if timers is not None and ev:
             timers.update({"plan": (t0, t1), "queried pieces: upload + records + thresholds + count": (t1, t2),
                            "count(+upload of the other slabs)": (t2, t3), "finalize": (t3, t4)})
+            timers["launches"] = eng.launches(max(n_count, 1), (-(-Q // 256) if max_cnt > 63 else 0) * max(n_count, 1)) \
+                + K + len(bounds) - 1 + 2 * (K - 1)
+            timers["slabs"] = K + len(bounds) - 1
+            timers["queried_rows"] = plan.n_queried
+            timers["query_groups"] = K
+        return res
+
+    def _host_grouped_ranks(self, plan, sizes, w, g_host, g_index_base, normalize, max_rank, timers, slab_rows, t01):
+        """Several ranks, every one with a pinned host shard: the grouped flow of
+        _evaluate_host_grouped with one record exchange per query block.  The records of a block are
+        a contiguous slice of every rank's local record array (padded to the longest slice, all-
+        gathered, merged into the block's piece of the global CSR), so thresholds and the first count
+        rectangles of block j exist while the rows of block j + 1 are still coming in."""
+        eng = self.engine
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ev = eng.event if timers is not None else None
+        mark = (lambda: ev()) if ev else (lambda: None)
+        g = sizes["groups"]
+        qb, K = g["qb"], len(g["qb"]) - 1
+        Q, G = plan.Q, plan.G
+        T, max_cnt = sizes["T_sum"], sizes["max_all"]
+        p0 = min(G, -(-max(plan.n_queried, 1) // 256) * 256)
+        gb = [0] + [min(p0, int(e)) for e in g["ends"][:K - 1]] + [p0]
+        for j in range(1, len(gb)):
+            gb[j] = max(gb[j], gb[j - 1])
+        bounds = [p0]
+        step = self._slab_rows(slab_rows, G - p0)
+        while bounds[-1] < G:
+            bounds.append(min(G, bounds[-1] + step))
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)                       # the queries are prepared (enqueued by the caller)
+        side = self._side_stream()
+        side.wait_event(start)
+        piece_in, slab_in = [], []
+        with torch.cuda.stream(side):
+            for j in range(K):
+                eng.prepare(plan, w, g_host, 1, gb[j], gb[j + 1] - gb[j], normalize, host_input=True)
+                e = torch.cuda.Event()
+                e.record(side)
+                piece_in.append(e)
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                eng.prepare(plan, w, g_host, 1, a, b - a, normalize, host_input=True)
+                e = torch.cuda.Event()
+                e.record(side)
+                slab_in.append(e)
+        cnt_all = sizes["cnt_all"]
+        total = cnt_all.to(torch.int64).sum(0)
+        thr_ofs = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
+        thr_ofs[1:] = torch.cumsum(total, 0)
+        thr_ofs = thr_ofs.to(torch.int32)
+        merged = torch.zeros((3, max(T, 1)), dtype=torch.int32, device=dev)
+        thr = eng.thresholds_alloc(T, Q, dev)
+        counts = torch.zeros(max(T, 1), dtype=torch.int32, device=dev)
+        n_count = 0
+        for j in range(K):
+            main.wait_event(piece_in[j])
+            recs = eng.extract(plan, w, g_index_base, q_row0=qb[j], q_nrows=qb[j + 1] - qb[j])
+            lo, hi = int(g["rec_lo"][j]), int(g["rec_lo"][j + 1])
+            padded = torch.zeros((3, max(int(g["gmax"][j]), 1)), dtype=torch.int32, device=dev)
+            padded[:, :hi - lo] = recs[:, lo:hi]
+            recs_all = self.coll.all_gather(padded)
+            a, b = int(g["gofs"][j]), int(g["gofs"][j + 1])
+            if b > a:
+                _, piece, _, _ = merge_records(cnt_all[:, qb[j]:qb[j + 1]], recs_all, sizes=(b - a, max_cnt))
+                merged[:, a:b] = piece
+                eng.thresholds_into(thr_ofs, merged, thr, qb[j], qb[j + 1] - qb[j])
+            else:
+                thr[0][qb[j]:qb[j + 1]] = 0
+            if T > 0:
+                if gb[j + 1] > gb[j]:
+                    eng.count(w, plan, thr_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=gb[j],
+                              g_nrows=gb[j + 1] - gb[j], q_row0=0, q_nrows=qb[j + 1])
+                    n_count += 1
+                if j > 0 and gb[j] > 0:
+                    eng.count(w, plan, thr_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=0, g_nrows=gb[j],
+                              q_row0=qb[j], q_nrows=qb[j + 1] - qb[j])
+                    n_count += 1
+        t2 = mark()
+        for i, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+            main.wait_event(slab_in[i])
+            if T > 0 and b > a:
+                eng.count(w, plan, thr_ofs, thr[0], thr[1], thr[2], counts, max_cnt, g_row0=a, g_nrows=b - a)
+                n_count += 1
+        t3 = mark()
+        self.coll.all_reduce_sum(counts)
+        t4 = mark()
+        res = self._finish(plan, thr, counts, thr_ofs, sizes["G_total"], max_rank)
+        t5 = mark()
+        if timers is not None and ev:
+            timers.update({"plan": t01, "queried pieces: upload + records + exchange + thresholds + count": (t01[1], t2),
+                           "count(+upload of the other slabs)": (t2, t3), "allreduce": (t3, t4), "finalize": (t4, t5)})
             timers["launches"] = eng.launches(max(n_count, 1), (-(-Q // 256) if max_cnt > 63 else 0) * max(n_count, 1)) \
                 + K + len(bounds) - 1 + 2 * (K - 1)
             timers["slabs"] = K + len(bounds) - 1

@@ -52,6 +52,23 @@ def _case():
     return qf, gf, qp, gp, qc, gc
 
 
+def _case_big():
+    """>= 2048 queries: the streamed evaluation runs its grouped flow (one record exchange per
+    query block); a fifth of the gallery has ids no query asks for, some ids have > 63 images."""
+    rng = np.random.default_rng(5)
+    Q, G, d, nid = 2300, 6001, 128, 150
+    centers = rng.standard_normal((nid, d)).astype(np.float32)
+    qp, gp = rng.integers(0, nid, Q), rng.integers(0, nid, G)
+    gp[gp < 8] = 3                               # one identity with ~300 gallery images (slab path)
+    gp[::5] += 4000
+    qp[:5] = 88888
+    qc, gc = rng.integers(0, 4, Q), rng.integers(0, 4, G)
+    qf = centers[qp % nid] + 2.0 * rng.standard_normal((Q, d)).astype(np.float32)
+    gf = centers[gp % nid] + 2.0 * rng.standard_normal((G, d)).astype(np.float32)
+    gf[100:140] = gf[5000:5040]                  # exact ties across shards
+    return qf, gf, qp, gp, qc, gc
+
+
 # ---------------------------------------------------------------------------------------------
 # two processes, one GPU
 # ---------------------------------------------------------------------------------------------
@@ -62,8 +79,17 @@ def _worker(rank, world, port, mode, out):
     try:
         from demo2_b200 import parallel
         torch.cuda.set_device(0)
-        qf, gf, qp, gp, qc, gc = _case()
-        if mode in ("sharded", "sharded_host"):
+        qf, gf, qp, gp, qc, gc = _case_big() if mode == "sharded_host_groups" else _case()
+        if mode == "sharded_host_groups":
+            lo, hi = parallel.shard_range(len(gp), world, rank)
+            ev = parallel.ShardedEvaluator(world=world, rank=rank, group=dist.group.WORLD)
+            timers = {}
+            res = ev.evaluate_host(torch.from_numpy(qf).pin_memory(), torch.from_numpy(gf[lo:hi].copy()).pin_memory(),
+                                   qp, gp[lo:hi], qc, gc[lo:hi], g_index_base=lo, normalize=True, slab_rows=512,
+                                   query_groups=2, timers=timers)
+            assert timers.get("query_groups") == 2
+            out[rank] = (res.cmc, float(res.mAP), res.num_valid, res.ap.cpu().numpy(), res.first.cpu().numpy())
+        elif mode in ("sharded", "sharded_host"):
             lo, hi = parallel.shard_range(len(gp), world, rank)
             ev = parallel.ShardedEvaluator(world=world, rank=rank, group=dist.group.WORLD)
             assert isinstance(ev.engine, parallel.CudaEngine)
@@ -103,12 +129,12 @@ def _spawn(mode, world=2):
     return out
 
 
-@pytest.mark.parametrize("mode", ["sharded", "sharded_host", "ddp"])
+@pytest.mark.parametrize("mode", ["sharded", "sharded_host", "sharded_host_groups", "ddp"])
 def test_two_process_evaluation_equals_single_gpu(mode):
     """Gallery sharded over two processes (CUDA engine, real process group) == one GPU, bit for bit:
     distances are position-independent and rank counts are additive over gallery shards."""
     from demo2_b200 import metrics
-    qf, gf, qp, gp, qc, gc = _case()
+    qf, gf, qp, gp, qc, gc = _case_big() if mode == "sharded_host_groups" else _case()
     assert (len(qp) + len(gp)) % 2 == 1          # the DDP sampler really pads
     single = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, normalize=True)
     out = _spawn(mode)
