@@ -1,6 +1,8 @@
 // extern "C" entry points for re-ranking and top-k (include/demo_b200.h).
 #include "gemm_epilogues.cuh"
 #include "gemm2_sm100.cuh"
+
+#include <cstdlib>
 #include "rerank.cuh"
 
 using namespace demo;
@@ -20,11 +22,16 @@ struct RrWs {
   RerankWs r;
 };
 
+// Leading dimension of the all-pairs matrix: rows start on 128-byte lines, so the store epilogue
+// can use its line-coalesced float4 path and a mirrored warp store never straddles five sectors
+// (N = 10 290 as the pitch: 41 M sector writes for 13 M sectors of data).
+inline long long e_pitch(int N) { return round_up(static_cast<long long>(N > 0 ? N : 1), 32ll); }
+
 size_t carve_rr(Carver& c, int N, int Q, int d, int k1, int k2, RrWs* w) {
   RrWs t;
   const size_t n = N > 0 ? N : 1;
   prep_carve(c, N, d > 0 ? d : 8, &t.a);
-  t.E = c.take<float>(n * n);
+  t.E = c.take<float>(n * static_cast<size_t>(e_pitch(N)));
   t.rowmax_key = c.take<unsigned>(n);
   t.rowmax = c.take<float>(n);
   rerank_carve(c, N, Q, k1, k2, &t.r);
@@ -53,6 +60,12 @@ int launch_sym_store(const PrepView& a, int a0, const PrepView& b, int b0, EpiSt
     s.tri = 1;
     s.tri_a0 = a0;
     s.tri_b0 = b0;
+    // whole square problem whose prepared rows stay in L2 (no need for the n-grouped raster) and
+    // few tiles per worker: folded enumeration of the upper triangle, every unit non-empty
+    static const bool no_fold = getenv("DEMO_NO_FOLD") != nullptr;   // A/B experiments
+    if (!no_fold && a0 == b0 && a.rows == b.rows && a.hi == b.hi &&
+        static_cast<size_t>(a.rows) * a.pitch * 4 <= (size_t(72) << 20))
+      s = make_folded_schedule2(a.rows);
     return launch_sqdist_gemm2<EpiStore>(ops, s, s.num_units, ep, stream);
   }
   DEMO_TRY(make_gemm_operands(a, b, &ops));
@@ -86,7 +99,7 @@ size_t carve_rr_shard(Carver& c, int N, int Q, int d, int k1, int k2, int rows_c
   RrShardWs t;
   const size_t n = N > 0 ? N : 1, rc = rows_cap > 0 ? rows_cap : 1;
   prep_carve(c, N, d > 0 ? d : 8, &t.a);
-  t.E = c.take<float>(rc * n);
+  t.E = c.take<float>(rc * static_cast<size_t>(e_pitch(N)));
   t.rowmax_key = c.take<unsigned>(rc);
   t.rowmax = c.take<float>(rc);
   rerank_carve(c, N, Q, k1, k2, &t.r);
@@ -142,7 +155,7 @@ int demo_rerank_shard_topk(const float* feat, int N, int Q, int d, int64_t ld, i
     // columns j >= i: local rows on the A side, stored in place
     EpiStore::Params ep;
     ep.out = w.E;
-    ep.ldo = N;
+    ep.ldo = e_pitch(N);
     ep.rowmax_key = w.rowmax_key;
     ep.sym_mask = 1;
     DEMO_TRY(launch_sym_store(rows, row0, w.a, 0, ep, stream));
@@ -152,18 +165,18 @@ int demo_rerank_shard_topk(const float* feat, int N, int Q, int d, int64_t ld, i
     // local rows are the B operand and every result is stored at the transposed position
     EpiStore::Params ep;
     ep.out = w.E;
-    ep.ldo = N;
+    ep.ldo = e_pitch(N);
     ep.rowmax_key = nullptr;
     ep.store_normal = 0;
     ep.sym_mirror = 1;
     ep.out_t = w.E;
-    ep.ldo_t = N;
+    ep.ldo_t = e_pitch(N);
     ep.rowmax_key_t = w.rowmax_key;
     DEMO_TRY(launch_sym_store(row_range(w.a, 0, row0 + nrows), 0, rows, row0, ep, stream));
   }
   keys_to_float_kernel2<<<ceil_div(nrows, 256), 256, 0, stream>>>(w.rowmax_key, w.rowmax, nrows);
   DEMO_CHECK_CUDA(cudaGetLastError());
-  return launch_topk_rows(w.E, N, nrows, N, w.rowmax, rerank_k(k1, k2), rank_rows, nullptr, stream);
+  return launch_topk_rows(w.E, e_pitch(N), nrows, N, w.rowmax, rerank_k(k1, k2), rank_rows, nullptr, stream);
 }
 
 // Stage 2: V rows of the local rows from the gathered neighbour lists (:51-71); writes rows
@@ -174,7 +187,7 @@ int demo_rerank_shard_krecip(int N, int Q, int d, int k1, int k2, int row0, int 
   RrShardWs w;
   DEMO_TRY(get_rr_shard(ws, ws_bytes, N, Q, d, k1, k2, rows_cap, &w));
   DEMO_REQUIRE(rank_all && v_idx && v_val && v_cnt, "rerank shard: null pointer");
-  return launch_krecip_rows(w.E, N, w.rowmax, rank_all, N, k1, k2, row0, nrows, v_idx, static_cast<__half*>(v_val),
+  return launch_krecip_rows(w.E, e_pitch(N), w.rowmax, rank_all, N, k1, k2, row0, nrows, v_idx, static_cast<__half*>(v_val),
                             v_cnt, w.r.rh_idx, w.r.rh_cnt, static_cast<cudaStream_t>(stream_));
 }
 
@@ -200,7 +213,7 @@ int demo_rerank_shard_jaccard(int N, int Q, int d, int k1, int k2, double lambda
   if (nq_local < 0) nq_local = 0;
   DEMO_REQUIRE(nq_local == 0 || (out_rows && ldo >= N - Q), "rerank shard: bad output");
   const int f_cap = k2 != 1 ? rerank_capq(N, k1, k2) : rerank_cap(k1);
-  return launch_jaccard_rows(w.E, N, w.rowmax, N, Q, lambda_value, row0, nq_local, f_idx,
+  return launch_jaccard_rows(w.E, e_pitch(N), w.rowmax, N, Q, lambda_value, row0, nq_local, f_idx,
                              static_cast<const __half*>(f_val), f_cnt, f_cap, w.r, out_rows, ldo,
                              static_cast<cudaStream_t>(stream_));
 }
@@ -234,27 +247,27 @@ int demo_rerank(const float* feat, int N, int Q, int d, int64_t ld, int flags, i
     // upper triangle only; every result is also stored at its transposed position
     EpiStore::Params ep;
     ep.out = w.E;
-    ep.ldo = N;
+    ep.ldo = e_pitch(N);
     ep.rowmax_key = fused_max ? w.rowmax_key : nullptr;
     ep.sym_mask = 1;
     ep.sym_mirror = 1;
     ep.out_t = w.E;
-    ep.ldo_t = N;
+    ep.ldo_t = e_pitch(N);
     ep.rowmax_key_t = fused_max ? w.rowmax_key : nullptr;
     DEMO_TRY(launch_sym_store(w.a, 0, w.a, 0, ep, stream));
     if (fused_max) {
       keys_to_float_kernel2<<<ceil_div(N, 256), 256, 0, stream>>>(w.rowmax_key, w.rowmax, N);
     } else {
       // X = D + local; E = X^T (see rerank.cu header).  Our GEMM output plays the role of D^T.
-      DEMO_TRY(launch_transpose_add(local_distmat, ld_local, w.E, N, N, true, stream));
-      DEMO_TRY(launch_rowmax(w.E, N, N, w.rowmax, stream));
+      DEMO_TRY(launch_transpose_add(local_distmat, ld_local, w.E, e_pitch(N), N, true, stream));
+      DEMO_TRY(launch_rowmax(w.E, e_pitch(N), N, w.rowmax, stream));
     }
   } else {
-    DEMO_TRY(launch_transpose_add(local_distmat, ld_local, w.E, N, N, false, stream));
-    DEMO_TRY(launch_rowmax(w.E, N, N, w.rowmax, stream));
+    DEMO_TRY(launch_transpose_add(local_distmat, ld_local, w.E, e_pitch(N), N, false, stream));
+    DEMO_TRY(launch_rowmax(w.E, e_pitch(N), N, w.rowmax, stream));
   }
   DEMO_CHECK_CUDA(cudaGetLastError());
-  return run_rerank_stages(w.E, N, w.rowmax, N, Q, k1, k2, lambda_value, w.r, out, ldo, stream);
+  return run_rerank_stages(w.E, e_pitch(N), w.rowmax, N, Q, k1, k2, lambda_value, w.r, out, ldo, stream);
 }
 
 // Same, starting from the reference's all-pairs matrix X = `original_dist` (before :46), e.g.
@@ -270,9 +283,9 @@ int demo_rerank_matrix(const float* X, int64_t ldx, int N, int Q, int k1, int k2
     set_error("rerank_matrix: workspace too small (%zu < %zu)", ws_bytes, c.off);
     return DEMO_ERR_WORKSPACE;
   }
-  DEMO_TRY(launch_transpose_add(X, ldx, w.E, N, N, false, stream));
-  DEMO_TRY(launch_rowmax(w.E, N, N, w.rowmax, stream));
-  return run_rerank_stages(w.E, N, w.rowmax, N, Q, k1, k2, lambda_value, w.r, out, ldo, stream);
+  DEMO_TRY(launch_transpose_add(X, ldx, w.E, e_pitch(N), N, false, stream));
+  DEMO_TRY(launch_rowmax(w.E, e_pitch(N), N, w.rowmax, stream));
+  return run_rerank_stages(w.E, e_pitch(N), w.rowmax, N, Q, k1, k2, lambda_value, w.r, out, ldo, stream);
 }
 
 // k smallest entries of every row, ascending by (value, column index); k <= 256.

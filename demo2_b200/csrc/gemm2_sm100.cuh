@@ -300,6 +300,7 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 int make_gemm2_operands(const PrepView& a, const PrepView& b, GemmOperands* ops);
 Schedule make_chunked_schedule2(int M, int N, int chunk_tiles, int d_pitch, int workers = 0);
 Schedule make_dense_schedule2(int M, int N);
+Schedule make_folded_schedule2(int N);
 bool prefer_pair_kernel(int M, int N);
 int max_active_pairs(const void* kernel, int smem);
 

@@ -62,8 +62,14 @@ struct EpiColumns {
 // STORE: materialise the matrix (euclidean_distance, cosine_*, re-ranking all-pairs)
 // ---------------------------------------------------------------------------------------
 struct EpiStore {
-  static constexpr int kStages = 4;
-  static constexpr int kSmemBytes = EpiColumns::kBytes;
+  // One 32 x 32 fp32 staging block (row stride 33) per epilogue warp: a thread owns a ROW of the
+  // tile, so storing straight from registers makes every store instruction touch 32 different
+  // 128-byte lines (ncu on the 10 290^2 all-pairs GEMM: lg_throttle stalls, tensor pipe 48 % active
+  // -- the accumulator buffers were not drained fast enough).  Through the staging block eight
+  // lanes write one 128-byte line: 4 lines per instruction.
+  static constexpr int kStageFloats = 32 * 33;
+  static constexpr int kStages = 3;   // 1-CTA kernel: 3 x 48 KB ring + the staging blocks
+  static constexpr int kSmemBytes = EpiColumns::kBytes + (kEpiThreads / 32) * kStageFloats * 4;
   struct Params {
     const float* a_norm;
     const float* a_inv;
@@ -91,9 +97,11 @@ struct EpiStore {
   const Params& p;
   EpiColumns cols;
   int epi_tid, row_in_tile, col0;
+  float* stage;   // this warp's staging block
 
   __device__ EpiStore(const Params& p_, uint8_t* smem, int epi_tid_, int row_in_tile_, int col0_)
-      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_) {}
+      : p(p_), cols(smem), epi_tid(epi_tid_), row_in_tile(row_in_tile_), col0(col0_),
+        stage(reinterpret_cast<float*>(smem + EpiColumns::kBytes) + (epi_tid_ >> 5) * kStageFloats) {}
 
   __device__ void stage_load(const TileInfo& t) { cols.load(t, epi_tid, p.b_norm, p.b_inv, nullptr, INFINITY); }
   __device__ void stage_store(int as) { cols.store(as, epi_tid); }
@@ -110,6 +118,11 @@ struct EpiStore {
     const int gr = p.a_global0 + row;                 // global index of this thread's row
     const int gc0 = p.b_global0 + t.n0 + col0;        // global index of this thread's first column
     float vmax = -INFINITY;
+    // coalesced path (warp-uniform conditions): the warp's 32 rows, 16-byte aligned row segments
+    const int lane = epi_tid & 31;
+    const int wrow0 = t.m0 + row_in_tile - lane;      // first row of this warp
+    float* wbase = p.out + static_cast<long long>(wrow0) * p.ldo + t.n0 + col0;
+    const bool warp_vec = (p.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(wbase) & 15u) == 0);
 #pragma unroll 1
     for (int c = 0; c < kEpiCols / 32; ++c) {
       if (c * 32 >= n_here) break;  // warp-uniform
@@ -129,7 +142,35 @@ struct EpiStore {
         }
       }
       const int nv = min(32, n_here - c * 32);
-      if (p.store_normal && row_ok) {
+      // whole 32 x 32 block valid (and on or above the diagonal): staged, line-coalesced stores
+      const bool block_ok = p.store_normal && nv == 32 &&
+                            (!p.sym_mask || p.a_global0 + wrow0 + 31 <= gc0 + c * 32);
+      if (block_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+        __syncwarp();
+        if (warp_vec) {                        // 8 lanes per 128-byte row segment, 4 rows per instruction
+          const int sub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + sub;
+            const float* sp = stage + rr * 33 + c4;
+            const float4 o = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            if (wrow0 + rr < p.M)
+              *reinterpret_cast<float4*>(wbase + static_cast<long long>(rr) * p.ldo + c * 32 + c4) = o;
+          }
+        } else {                               // rows not 16-byte aligned: one contiguous 128-byte row segment per instruction
+          const int nrow = min(32, p.M - wrow0);
+#pragma unroll 8
+          for (int rr = 0; rr < nrow; ++rr)
+            wbase[static_cast<long long>(rr) * p.ldo + c * 32 + lane] = stage[rr * 33 + lane];
+        }
+        __syncwarp();
+        if (p.rowmax_key && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j]);
+        }
+      } else if (p.store_normal && row_ok) {
         const int gc = gc0 + c * 32;                  // column j of this chunk has global index gc + j
         const bool all_upper = !p.sym_mask || gr <= gc;
         if (nv == 32 && vec_ok && all_upper) {

@@ -94,6 +94,17 @@ Schedule make_dense_schedule2(int M, int N) {
   return s;
 }
 
+// Upper triangle of the square tile grid of an N x N all-pairs problem for the CTA-pair kernel
+// (256 x 256 tiles), rows folded in pairs: only non-empty units, so the persistent workers get
+// equal shares (the dense raster with empty lower-triangle units gave every worker a random
+// 11.6 +- 2.4 of the 861 tiles at N = 10 290: the slowest pair set the time).
+Schedule make_folded_schedule2(int N) {
+  Schedule s = make_dense_schedule2(N, N);
+  s.mode = 3;
+  s.num_units = ceil_div(s.m_blocks, 2) * (s.n_tiles + 1);
+  return s;
+}
+
 // The pair kernel pays off once there is enough work to fill the machine with 256 x 256 tiles.
 bool prefer_pair_kernel(int M, int N) {
   static const bool force_1cta = getenv("DEMO_STORE_1CTA") != nullptr;  // A/B timing experiments

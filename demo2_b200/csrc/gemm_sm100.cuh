@@ -41,7 +41,8 @@ struct WorkUnit {
 
 // How units are enumerated.  All three roles of a CTA walk the same sequence.
 struct Schedule {
-  int mode = 0;          // 0: dense tiles, n-grouped raster; 1: chunked rows of tiles; 2: device list
+  int mode = 0;          // 0: dense tiles, n-grouped raster; 1: chunked rows of tiles; 2: device list;
+                         // 3: upper triangle of a square tile grid, rows folded in pairs (make_folded_schedule2)
   int M = 0, N = 0;      // valid rows of A / B
   int m_blocks = 0, n_tiles = 0;
   int group_n = 8;       // mode 0: n-tiles per raster group
@@ -102,6 +103,21 @@ __device__ __forceinline__ WorkUnit schedule_get(const Schedule& s, int u) {
     w.m0 = m * s.m_block_rows;
     w.n0 = c * s.chunk_tiles * kBN;
     w.n_rows = min(s.chunk_tiles * kBN, s.N - w.n0);
+  } else if (s.mode == 3) {
+    // square grid (m_blocks == n_tiles, square tiles): row i holds the tiles n >= i; rows i and
+    // m_blocks - 1 - i together hold n_tiles + 1 tiles, so "super-row" sr = u / (n_tiles + 1) is
+    // a closed form and every unit is non-empty (except the second half of the middle row of an
+    // odd grid)
+    const int per = s.n_tiles + 1;
+    const int sr = u / per, t = u - sr * per;
+    int m = sr, n = sr + t;
+    if (t >= s.n_tiles - sr) {
+      m = s.m_blocks - 1 - sr;
+      n = m + (t - (s.n_tiles - sr));
+    }
+    w.m0 = m * s.m_block_rows;
+    w.n0 = n * kBN;
+    w.n_rows = (t >= s.n_tiles - sr && m == sr) ? 0 : min(kBN, s.N - w.n0);
   } else {
     const int4 e = __ldg(s.list + u);
     w.m0 = e.x * kBM;

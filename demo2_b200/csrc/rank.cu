@@ -247,6 +247,9 @@ __device__ __forceinline__ bool lex_before(float da, int ga, float db, int gb) {
 // global memory); longer lists fall back to global reads.
 constexpr int kThrWarps = 4;
 constexpr int kThrStage = 256;
+constexpr int kThrLong = 64;          // lists longer than this: one block per query
+constexpr int kThrLongThreads = 128;
+constexpr int kThrLongStage = 1024;
 
 __global__ void __launch_bounds__(kThrWarps * 32)
 build_thresholds_kernel(const int* __restrict__ rec_ofs, const float* __restrict__ rec_dist,
@@ -261,6 +264,7 @@ build_thresholds_kernel(const int* __restrict__ rec_ofs, const float* __restrict
   const int lane = threadIdx.x & 31;
   if (i >= Q) return;
   const int s0 = rec_ofs[i], n = rec_ofs[i + 1] - s0;
+  if (n > kThrLong) return;                    // long lists: build_thresholds_long_kernel
   const bool staged = n <= kThrStage;
   if (staged) {
     for (int a = lane; a < n; a += 32) {
@@ -295,6 +299,62 @@ build_thresholds_kernel(const int* __restrict__ rec_ofs, const float* __restrict
   if (lane == 0) thr_cnt[i] = npos;
 }
 
+// Long lists (identities with hundreds of gallery images): the same rank-by-counting with one
+// BLOCK per query -- the O(n^2) comparisons of a 171-record list kept a single warp busy for
+// 1 000 dependent iterations per lane, and with one warp per query only ~12 warps per SM were in
+// flight (68 us for RGBNT100's 1 715 queries; 4 warps per query: latency hidden).
+__global__ void __launch_bounds__(kThrLongThreads)
+build_thresholds_long_kernel(const int* __restrict__ rec_ofs, const float* __restrict__ rec_dist,
+                             const int* __restrict__ rec_gidx, const int* __restrict__ rec_junk,
+                             int Q, int* __restrict__ thr_cnt, float* __restrict__ thr_val,
+                             int* __restrict__ thr_gidx, int* __restrict__ thr_junk) {
+  __shared__ float s_d[kThrLongStage];
+  __shared__ int s_g[kThrLongStage];
+  __shared__ int s_j[kThrLongStage];
+  __shared__ int s_npos[kThrLongThreads / 32];
+  const int i = blockIdx.x, t = threadIdx.x;
+  const int s0 = rec_ofs[i], n = rec_ofs[i + 1] - s0;
+  if (n <= kThrLong) return;                   // build_thresholds_kernel
+  const bool staged = n <= kThrLongStage;
+  if (staged) {
+    for (int a = t; a < n; a += kThrLongThreads) {
+      s_d[a] = rec_dist[s0 + a];
+      s_g[a] = rec_gidx[s0 + a];
+      s_j[a] = rec_junk[s0 + a];
+    }
+  }
+  __syncthreads();
+  const float* d = staged ? s_d : rec_dist + s0;
+  const int* g = staged ? s_g : rec_gidx + s0;
+  const int* jk = staged ? s_j : rec_junk + s0;
+  int npos = 0;
+  for (int a = t; a < n; a += kThrLongThreads) {
+    if (jk[a]) continue;
+    const float da = d[a];
+    const int ga = g[a];
+    int pos_before = 0, junk_before = 0;
+    for (int b = 0; b < n; ++b) {
+      const bool before = lex_before(d[b], g[b], da, ga);
+      const int jb = jk[b];
+      pos_before += (before && !jb) ? 1 : 0;
+      junk_before += (before && jb) ? 1 : 0;
+    }
+    thr_val[s0 + pos_before] = da;
+    thr_gidx[s0 + pos_before] = ga;
+    thr_junk[s0 + pos_before] = junk_before;
+    ++npos;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
+  if ((t & 31) == 0) s_npos[t >> 5] = npos;
+  __syncthreads();
+  if (t == 0) {
+    int tot = 0;
+    for (int w = 0; w < kThrLongThreads / 32; ++w) tot += s_npos[w];
+    thr_cnt[i] = tot;
+  }
+}
+
 }  // namespace
 
 int launch_fill_records(const PlanView& p, const int* q_cam, const int* g_cam, int g_index_base,
@@ -320,6 +380,9 @@ int launch_build_thresholds(const int* rec_ofs, const float* rec_dist, const int
   if (Q <= 0) return DEMO_OK;
   build_thresholds_kernel<<<ceil_div(Q, kThrWarps), kThrWarps * 32, 0, stream>>>(rec_ofs, rec_dist, rec_gidx, rec_junk, Q,
                                                                      thr_cnt, thr_val, thr_gidx, thr_junk);
+  // every query belongs to exactly one of the two kernels (the blocks of the other return at once)
+  build_thresholds_long_kernel<<<Q, kThrLongThreads, 0, stream>>>(rec_ofs, rec_dist, rec_gidx, rec_junk, Q, thr_cnt,
+                                                                  thr_val, thr_gidx, thr_junk);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }
@@ -570,7 +633,7 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
                        const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
                        const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int small_too,
                        int hist_rows, CountRows rows) {
-  extern __shared__ __align__(16) unsigned char s_hist8[];   // [hist_rows][256] u8, column = thread (>= 33 rows: scratch)
+  extern __shared__ __align__(16) unsigned char s_hist8[];   // [hist_rows][256] u8, column = thread (>= 4 rows: scratch)
   __shared__ float s_thr[kC8Bins];                           // padded with +inf
   __shared__ int s_tg[kC8Bins];
   __shared__ unsigned short s_fine[kC8Fine];                 // first threshold of the bin | count << 8
@@ -592,19 +655,30 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
   auto fine_of = [&](float x) -> int {   // monotone in x for x >= tmin
     return min(kC8Fine - 1, __float2int_rz((x - tmin) * scale));
   };
-  // first[j] = index of the first threshold whose bin is >= j (scratch: the histogram area): thread k
-  // owns the bins (f(t_{k-1}), f(t_k)]; f(t_0) = 0 and every bin above f(t_last) gets nthr
-  unsigned* first = reinterpret_cast<unsigned*>(s_hist8);
-  if (t < nthr) {
-    const int jk = fine_of(s_thr[t]);
-    const int jp = t > 0 ? fine_of(s_thr[t - 1]) : -1;
-    for (int j = jp + 1; j <= jk; ++j) first[j] = static_cast<unsigned>(t);
-  }
-  if (t == 0)
-    for (int j = fine_of(tmax) + 1; j <= kC8Fine; ++j) first[j] = static_cast<unsigned>(nthr);
+  // s_fine[j] = (index of the first threshold whose bin is >= j) | (thresholds in bin j) << 8.
+  // The thresholds' own bins (scratch: the head of the histogram area) are non-decreasing, so
+  // every bin finds its first threshold by bisection -- 8 bins per thread, no serial fill of the
+  // gaps between distant thresholds.
+  int* tbin = reinterpret_cast<int*>(s_hist8);
+  if (t < nthr) tbin[t] = fine_of(s_thr[t]);
   __syncthreads();
-  for (int j = t; j < kC8Fine; j += kC8Threads)
-    s_fine[j] = static_cast<unsigned short>(first[j] | ((first[j + 1] - first[j]) << 8));
+  {
+    // thread t owns the 8 consecutive bins [8t, 8t + 8): one bisection, then a walk
+    const int j0 = t * (kC8Fine / kC8Threads);
+    int lo = 0, hi = nthr;                     // #{k : tbin[k] < j0}
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (tbin[mid] < j0) lo = mid + 1; else hi = mid;
+    }
+    int f = lo;
+#pragma unroll 1
+    for (int j = j0; j < j0 + kC8Fine / kC8Threads; ++j) {
+      int f1 = f;
+      while (f1 < nthr && tbin[f1] <= j) ++f1;
+      s_fine[j] = static_cast<unsigned short>(f | ((f1 - f) << 8));
+      f = f1;
+    }
+  }
   __syncthreads();
   {
     uint4* h = reinterpret_cast<uint4*>(s_hist8);
@@ -668,15 +742,18 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
   };
   auto flush = [&]() {                         // private columns -> u32 totals, columns back to zero
     __syncthreads();
-    const int warp = t >> 5, lane = t & 31;
-    for (int b = warp; b <= nthr; b += kC8Threads / 32) {
-      uint2* p = reinterpret_cast<uint2*>(s_hist8 + b * kC8Threads + 8 * lane);
-      const uint2 x = *p;
-      unsigned sum = __dp4a(x.x, 0x01010101u, 0u) + __dp4a(x.y, 0x01010101u, 0u);
+    if (t <= nthr) {                           // one bin (a 256-byte row) per thread, 16-byte chunks rotated by
+      uint4* rowp = reinterpret_cast<uint4*>(s_hist8 + t * kC8Threads);   // the thread index: conflict-free
+      unsigned sum = 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == 0) s_tot[b] += sum;
-      *p = make_uint2(0u, 0u);
+      for (int c = 0; c < 16; ++c) {
+        const int k = (c + t) & 15;
+        const uint4 x = rowp[k];
+        sum += __dp4a(x.x, 0x01010101u, 0u) + __dp4a(x.y, 0x01010101u, 0u) + __dp4a(x.z, 0x01010101u, 0u) +
+               __dp4a(x.w, 0x01010101u, 0u);
+        rowp[k] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      s_tot[t] += sum;
     }
     __syncthreads();
   };

@@ -277,10 +277,10 @@ class CudaEngine:
 
     def launches(self, count_launches=1, slab_blocks=0):
         # plan: iota, gallery key / unkey, ranges, band list | 2x prep, gidx, fill records, extract GEMM |
-        # thresholds | per count launch: count GEMM, tie resolver, conditional tie-fix GEMM (+ per
+        # thresholds (short + long lists) | per count launch: count GEMM, tie resolver, conditional tie-fix GEMM (+ per
         # flagged 256-row block: store GEMM + 2 streaming count kernels) | per-query AP, reduce
         # (CUB sort/scan kernels and memsets not counted)
-        return 5 + 5 + 1 + 3 * count_launches + 3 * slab_blocks + 2
+        return 5 + 5 + 2 + 3 * count_launches + 3 * slab_blocks + 2
 
     @staticmethod
     def event():
