@@ -81,6 +81,7 @@ def _worker(rank, world, port, mode, out):
         torch.cuda.set_device(0)
         qf, gf, qp, gp, qc, gc = _case_big() if mode == "sharded_host_groups" else _case()
         if mode == "sharded_host_groups":
+            parallel.MIN_PIECE_ROWS = 64          # the library only groups when the pieces are large; force it here
             lo, hi = parallel.shard_range(len(gp), world, rank)
             ev = parallel.ShardedEvaluator(world=world, rank=rank, group=dist.group.WORLD)
             timers = {}
@@ -184,13 +185,16 @@ def test_streamed_host_evaluation_equals_device_evaluation(slab_rows):
     assert float(res2.mAP) == float(single.mAP)
 
 
-@pytest.mark.parametrize("Q,G,nid,groups", [(2600, 12000, 400, 4), (4200, 9000, 700, 3), (2100, 8000, 30, 2)])
-def test_streamed_host_evaluation_query_groups(Q, G, nid, groups):
+@pytest.mark.parametrize("Q,G,nid,groups,force", [(2600, 12000, 400, 4, True), (4200, 9000, 700, 3, True),
+                                                   (2100, 8000, 30, 2, True), (2600, 12000, 400, 4, False)])
+def test_streamed_host_evaluation_query_groups(Q, G, nid, groups, force, monkeypatch):
     """One GPU, >= 2048 queries: the queried gallery rows are pulled in per block of pid-sorted
     queries and the count GEMM starts on the first block's rectangle while the others are still in
     flight (ShardedEvaluator._evaluate_host_grouped).  The rectangles tile Q x G exactly once:
     same integers as the device-resident evaluation (nid = 30: ~270 gallery images per id, slab path)."""
     from demo2_b200 import metrics, parallel
+    if force:
+        monkeypatch.setattr(parallel, "MIN_PIECE_ROWS", 64)   # small test galleries: force the grouped flow
     rng = np.random.default_rng(Q + G)
     d = 128
     centers = rng.standard_normal((nid, d)).astype(np.float32)
@@ -206,7 +210,7 @@ def test_streamed_host_evaluation_query_groups(Q, G, nid, groups):
     timers = {}
     res = ev.evaluate_host(torch.from_numpy(qf).pin_memory(), torch.from_numpy(gf).pin_memory(), qp, gp, qc, gc,
                            normalize=True, slab_rows=2048, timers=timers, query_groups=groups)
-    assert timers["query_groups"] >= 2
+    assert timers["query_groups"] >= 2 if force else timers["query_groups"] == 1   # small pieces are merged
     np.testing.assert_array_equal(res.cmc, single.cmc)
     assert float(res.mAP) == float(single.mAP)
     np.testing.assert_array_equal(res.ap.cpu().numpy(), single.ap.cpu().numpy())
@@ -214,6 +218,27 @@ def test_streamed_host_evaluation_query_groups(Q, G, nid, groups):
     r1, r2 = res.positive_ranks(), single.positive_ranks()
     for a, b in zip(r1, r2):
         np.testing.assert_array_equal(a, b)
+
+
+def test_streamed_host_evaluation_no_query_id_in_gallery(monkeypatch):
+    """Grouped flow with T = 0 (no query identity appears in the gallery): nothing to rank, zero
+    valid queries -- the same answer as the device-resident evaluation."""
+    from demo2_b200 import metrics, parallel
+    monkeypatch.setattr(parallel, "MIN_PIECE_ROWS", 0)
+    rng = np.random.default_rng(0)
+    Q, G, d = 2100, 3000, 64
+    qf = rng.standard_normal((Q, d)).astype(np.float32)
+    gf = rng.standard_normal((G, d)).astype(np.float32)
+    qp, gp = rng.integers(0, 50, Q), rng.integers(100, 150, G)
+    qc, gc = rng.integers(0, 3, Q), rng.integers(0, 3, G)
+    single = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, normalize=True)
+    assert single.num_valid == 0
+    timers = {}
+    res = parallel.ShardedEvaluator().evaluate_host(torch.from_numpy(qf).pin_memory(), torch.from_numpy(gf).pin_memory(),
+                                                    qp, gp, qc, gc, normalize=True, timers=timers, query_groups=2)
+    assert timers["query_groups"] == 2 and res.num_valid == 0
+    np.testing.assert_array_equal(res.cmc, single.cmc)
+    np.testing.assert_array_equal(res.first.cpu().numpy(), single.first.cpu().numpy())
 
 
 # ---------------------------------------------------------------------------------------------

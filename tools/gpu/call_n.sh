@@ -7,7 +7,7 @@ import bench
 dev = torch.device('cuda')
 peaks = bench.load_peaks()
 for rep in range(2):
-    o = bench.other_workloads(dev, peaks, with_cpu=(rep == 0))
+    o = bench.other_workloads(dev, peaks)
     print(rep, {k: round(v['ms'], 4) for k, v in o.items() if isinstance(v, dict) and 'ms' in v})
 PY
 cat gpurun_out/r2n_other.log | tail -5
