@@ -413,7 +413,7 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
   const int tbase = thr_ofs[i] + window * kCmWin;
   const int nthr = max(0, min(kCmWin, thr_cnt[i] - window * kCmWin));
   if (nthr == 0) return;
-  // rows with <= 255 finite thresholds belong to count_matrix63_kernel / count_matrix255_kernel
+  // rows with <= 255 finite thresholds belong to count_matrix255_kernel
   if (thr_cnt[i] <= 255 && isfinite(thr_val[thr_ofs[i] + thr_cnt[i] - 1])) return;
   for (int k = t; k < nthr; k += kCmThreads) {
     s_thr[k] = thr_val[tbase + k];
@@ -474,176 +474,46 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
   }
 }
 
-// Fast path for rows with at most 63 finite thresholds (the common case): the technique of the
-// GEMM count epilogue on a materialised row.  The thresholds are uniform over the block, so the
-// top three levels of the bisection live in registers and the lower three are read from a small
-// table.  Table layout (floats): [0] = -inf sentinel, [1 + k] = t_k for k < 32, [33] = copy of
-// t_31, [34 + (k - 32)] = t_k for k >= 32: the one-word shift of the upper half makes every tree
-// level touch distinct banks (or the same word), and the word below any slot is the threshold
-// below it (tie probe).  The search carries the byte address of the slot; each thread owns a
-// private column of the [64][256] histogram -- no atomics; float4 row loads; 4 B per pair read once.
-constexpr int kCfThreads = 256;
-constexpr int kCfWin = 63;
-
-__global__ void __launch_bounds__(kCfThreads)
-count_matrix63_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
-                      const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
-                      const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
-                      const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, CountRows rows) {
-  extern __shared__ unsigned short s_hist[];    // [64][kCfThreads] u16, column = thread (G <= 2^24 per launch)
-  __shared__ float s_tab[68];
-  __shared__ int s_tg[64];
-  __shared__ unsigned s_tot[64];
-  const int i = rows.row0 + blockIdx.x, t = threadIdx.x;   // i: sorted query
-  if (rows.blk_flag && rows.blk_flag[i >> 8] == 0) return;   // block handled by the fused GEMM epilogue
-  const int nthr = thr_cnt[i];
-  if (nthr <= 0 || nthr > kCfWin) return;       // larger rows: count_matrix_kernel
-  const int tbase = thr_ofs[i];
-  if (!isfinite(__ldg(thr_val + tbase + nthr - 1))) return;
-  if (t < 64) {
-    const float v = t < nthr ? __ldg(thr_val + tbase + t) : INFINITY;
-    s_tab[t < 32 ? 1 + t : 2 + t] = v;
-    if (t == 31) s_tab[33] = v;
-    if (t == 0) s_tab[0] = -INFINITY;
-    s_tg[t] = t < nthr ? __ldg(thr_gidx + tbase + t) : -1;
-  }
-#pragma unroll 8
-  for (int b = 0; b < 64; ++b) s_hist[b * kCfThreads + t] = 0;
-  __syncthreads();
-  const float t31 = s_tab[32], t15 = s_tab[16], t47 = s_tab[49];
-  const float t7 = s_tab[8], t23 = s_tab[24], t39 = s_tab[41], t55 = s_tab[57];
-  const uint32_t tab0 = smem_u32(s_tab) + 4;    // address of slot 0
-  const uint32_t hist0 = smem_u32(s_hist) + 2 * t;
-  const float* row = distmat + static_cast<long long>(q_perm ? q_perm[i] : static_cast<int>(blockIdx.x)) * ld;
-
-  // byte address of slot b = #{thresholds <= d}
-  auto search = [&](float d) -> uint32_t {
-    const bool p1 = t31 <= d;
-    uint32_t a = p1 ? tab0 + 33 * 4 : tab0;
-    const float u2 = p1 ? t47 : t15;
-    const bool p2 = u2 <= d;
-    a += p2 ? 64 : 0;
-    const float hi3 = p2 ? t55 : t39, lo3 = p2 ? t23 : t7;
-    a += ((p1 ? hi3 : lo3) <= d) ? 32 : 0;
-    float u;
-    asm("ld.shared.f32 %0, [%1+12];" : "=f"(u) : "r"(a));
-    a += (u <= d) ? 16 : 0;
-    asm("ld.shared.f32 %0, [%1+4];" : "=f"(u) : "r"(a));
-    a += (u <= d) ? 8 : 0;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(u) : "r"(a));
-    a += (u <= d) ? 4 : 0;
-    return a;
-  };
-  auto bump = [&](uint32_t a, float d, int g) {
-    int b = static_cast<int>(a - tab0) >> 2;
-    b -= b > 32 ? 1 : 0;                         // undo the one-word shift of the upper half
-    float below;
-    asm("ld.shared.f32 %0, [%1+-4];" : "=f"(below) : "r"(a));
-    if (below == d) {                            // bit-equal to a threshold: (distance, index) order
-      const int gi = rows.col_gidx ? __ldg(rows.col_gidx + g) : g_index_base + g;
-      while (b > 0 && s_tab[b <= 32 ? b : b + 1] == d && s_tg[b - 1] > gi) --b;
-    }
-    const uint32_t h = hist0 + static_cast<uint32_t>(b) * (kCfThreads * 2);
-    unsigned c;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c) : "r"(h));
-    c += 1u;
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(h), "r"(c));
-  };
-
-  // head up to the first 16-byte aligned element, float4 body (8 independent searches in flight), scalar tail
-  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(row) >> 2) & 3u);
-  const int head = min(G, (4 - mis) & 3);
-  if (t < head) {
-    const float d = __ldg(row + t);
-    bump(search(d), d, t);
-  }
-  const int nvec = (G - head) >> 2;
-  const float4* row4 = reinterpret_cast<const float4*>(row + head);
-  int v = t;
-  for (; v + kCfThreads < nvec; v += 2 * kCfThreads) {
-    const float4 x = __ldcs(row4 + v), y = __ldcs(row4 + v + kCfThreads);
-    const float d[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-    uint32_t a[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] = search(d[e]);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) bump(a[e], d[e], head + 4 * (v + (e >> 2) * kCfThreads) + (e & 3));
-  }
-  for (; v < nvec; v += kCfThreads) {
-    const float4 x = __ldcs(row4 + v);
-    const float d[4] = {x.x, x.y, x.z, x.w};
-    uint32_t a[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) a[e] = search(d[e]);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) bump(a[e], d[e], head + 4 * v + e);
-  }
-  const int tail0 = head + 4 * nvec;
-  if (tail0 + t < G) {
-    const float d = __ldg(row + tail0 + t);
-    bump(search(d), d, tail0 + t);
-  }
-  __syncthreads();
-  // bucket totals: warp w sums buckets 8w .. 8w+7 over the 256 columns
-  const int warp = t >> 5, lane = t & 31;
-  for (int b = warp * 8; b < warp * 8 + 8; ++b) {
-    unsigned sum = 0;
-#pragma unroll
-    for (int c = lane; c < kCfThreads; c += 32) sum += s_hist[b * kCfThreads + c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) s_tot[b] = sum;
-  }
-  __syncthreads();
-  if (t < 32) {                                  // counts[k] += sum_{b <= k} tot[b]
-    unsigned a = s_tot[2 * t], c = s_tot[2 * t + 1];
-    unsigned incl = a + c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
-      if (t >= o) incl += x;
-    }
-    const unsigned before = incl - a - c;
-    if (2 * t < nthr && before + a) atomicAdd(counts + tbase + 2 * t, before + a);
-    if (2 * t + 1 < nthr && incl) atomicAdd(counts + tbase + 2 * t + 1, incl);
-  }
-}
-
-
-// Rows with 64 .. 255 finite thresholds (identities with a few hundred gallery images, e.g.
-// RGBNT100's ~171 per id), and shorter rows when the u16 kernel above cannot be used.  A bisection
-// over 255 slots would cost five dependent shared-memory probes at random addresses; instead the
-// value range [t_0, t_last] of the row's thresholds is cut into kC8Fine equal bins by ONE monotone
-// arithmetic map f(x) = min(F-1, int((x - t_0) * s)): thresholds and elements go through the same
-// expression, so f(thr) < f(x) implies thr < x and f(thr) > f(x) implies thr > x -- only the
-// thresholds that share the element's bin are compared explicitly, and an element can only tie
-// with a threshold of its own bin.  Common case, branch-free: one u16 table entry (first threshold
-// of the bin | how many), one probe of that threshold, a private u8 histogram column (no atomics;
-// flushed into u32 totals every 240 elements per thread, before a counter can wrap).  Bins with
-// two or more thresholds and bit-ties take a slow path (bisection inside the bin + the
-// (distance, index) rule).  4 B per pair read once.
+// Rows with up to 255 finite thresholds (everything from the 17 positives per query of the
+// benchmark to RGBNT100's ~171 images per id).  A bisection over the thresholds costs one dependent
+// shared-memory probe per level at random addresses (the 63-threshold kernel this replaces:
+// 3 register + 3 table levels, 41 warp instructions per 32 elements, 1.39 ms for 4096 x 262 144;
+// 255 thresholds would need five table levels).  Instead the value range [t_0, t_last] of the row's
+// thresholds is cut into kC8Fine equal bins by ONE monotone arithmetic map
+// f(x) = min(F + 1, u32(fma(x, s, o))): thresholds and elements go through the same expression,
+// so f(thr) < f(x) implies thr < x and f(thr) > f(x) implies thr > x -- only the thresholds that
+// share the element's bin are compared explicitly, and an element can only tie with a threshold
+// of its own bin.  Common case, branch-free: one u16 table entry (first threshold of the bin | how
+// many), one probe of that threshold, a private u8 histogram column (no atomics; flushed into u32
+// totals every 240 elements per thread, before a counter can wrap).  Bins with two or more
+// thresholds and bit-ties take a slow path (bisection inside the bin + the (distance, index)
+// rule).  4 B per pair read once; 26-29 warp instructions per 32 elements: 1.23 ms (3.5 TB/s) at
+// ~20 and 1.67 ms (2.6 TB/s) at ~170 thresholds per row for 4096 x 262 144.
 constexpr int kC8Threads = 256;
-constexpr int kC8Fine = 2048;
+constexpr int kC8Fine = 4096;
 constexpr int kC8Bins = 256;
+#ifndef DEMO_C8_BATCH8
+#define DEMO_C8_BATCH8 0
+#endif
+constexpr bool kC8Batch8 = DEMO_C8_BATCH8 != 0;   // 8 look-ups in flight before the (ordered) histogram updates
 constexpr int kC8FlushIters = 30;   // 8 elements per thread and iteration: 240 (+ head / tail / remainder <= 10) <= 255
 
 __global__ void __launch_bounds__(kC8Threads, 4)
 count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
                        const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
                        const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
-                       const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int small_too,
-                       int hist_rows, CountRows rows) {
+                       const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int hist_rows,
+                       CountRows rows) {
   extern __shared__ __align__(16) unsigned char s_hist8[];   // [hist_rows][256] u8, column = thread (>= 4 rows: scratch)
   __shared__ float s_thr[kC8Bins];                           // padded with +inf
   __shared__ int s_tg[kC8Bins];
-  __shared__ unsigned short s_fine[kC8Fine];                 // first threshold of the bin | count << 8
+  __shared__ unsigned short s_fine[kC8Fine + 2];             // first threshold of the bin | count << 8
   __shared__ unsigned s_tot[kC8Bins];
   __shared__ unsigned s_warp[kC8Threads / 32];
   const int i = rows.row0 + blockIdx.x, t = threadIdx.x;     // i: sorted query
   if (rows.blk_flag && rows.blk_flag[i >> 8] == 0) return;   // block handled by the fused GEMM epilogue
   const int nthr = thr_cnt[i];
   if (nthr <= 0 || nthr > kC8Bins - 1 || nthr >= hist_rows) return;   // longer rows: count_matrix_kernel
-  if (nthr <= kCfWin && !small_too) return;                  // count_matrix63_kernel
   const int tbase = thr_ofs[i];
   if (!isfinite(__ldg(thr_val + tbase + nthr - 1))) return;
   s_thr[t] = t < nthr ? __ldg(thr_val + tbase + t) : INFINITY;
@@ -651,20 +521,26 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
   s_tot[t] = 0u;
   __syncthreads();
   const float tmin = s_thr[0], tmax = s_thr[nthr - 1];
-  const float scale = tmax > tmin ? static_cast<float>(kC8Fine) / (tmax - tmin) : 0.f;
-  auto fine_of = [&](float x) -> int {   // monotone in x for x >= tmin
-    return min(kC8Fine - 1, __float2int_rz((x - tmin) * scale));
+  // bin of x: min(F + 1, u32(fma(x, scale, off))) -- ONE rounding, monotone in x; the unsigned
+  // conversion saturates everything below t_0 to bin 0, bin F + 1 lies beyond every threshold
+  // (t_last lands in bin F - 1 or F).  Equal thresholds (or a single one): a tiny positive range,
+  // so that the elements above it still leave the thresholds' bin.
+  const float range = fmaxf(tmax - tmin, fmaxf(fabsf(tmin) * 9.5e-7f, 1e-30f));
+  const float scale = static_cast<float>(kC8Fine) / range, off = -tmin * scale;
+  auto fine_of = [&](float x) -> unsigned {
+    return min(__float2uint_rz(fmaf(x, scale, off)), static_cast<unsigned>(kC8Fine + 1));
   };
   // s_fine[j] = (index of the first threshold whose bin is >= j) | (thresholds in bin j) << 8.
   // The thresholds' own bins (scratch: the head of the histogram area) are non-decreasing, so
   // every bin finds its first threshold by bisection -- 8 bins per thread, no serial fill of the
   // gaps between distant thresholds.
   int* tbin = reinterpret_cast<int*>(s_hist8);
-  if (t < nthr) tbin[t] = fine_of(s_thr[t]);
+  if (t < nthr) tbin[t] = static_cast<int>(fine_of(s_thr[t]));
   __syncthreads();
   {
-    // thread t owns the 8 consecutive bins [8t, 8t + 8): one bisection, then a walk
-    const int j0 = t * (kC8Fine / kC8Threads);
+    // thread t owns the consecutive bins [9t, 9t + 9) of the F + 2: one bisection, then a walk
+    constexpr int kPer = (kC8Fine + 2 + kC8Threads - 1) / kC8Threads;
+    const int j0 = t * kPer, j1 = min(j0 + kPer, kC8Fine + 2);
     int lo = 0, hi = nthr;                     // #{k : tbin[k] < j0}
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -672,7 +548,7 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
     }
     int f = lo;
 #pragma unroll 1
-    for (int j = j0; j < j0 + kC8Fine / kC8Threads; ++j) {
+    for (int j = j0; j < j1; ++j) {
       int f1 = f;
       while (f1 < nthr && tbin[f1] <= j) ++f1;
       s_fine[j] = static_cast<unsigned short>(f | ((f1 - f) << 8));
@@ -693,12 +569,14 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
 
   // branch-free part: slot of the element, or "needs the slow path" (bit 31)
   auto fast_pos = [&](float d) -> unsigned {
-    const unsigned e = d >= tmin ? s_fine[fine_of(d)] : 0u;
-    const unsigned base = e & 0xffu, nin = e >> 8;
-    const float tv = s_thr[base];              // first threshold of the bin (a later one, > d, when the bin is empty)
-    unsigned pos = base + ((nin != 0u && tv <= d) ? 1u : 0u);
-    pos |= (nin > 1u || tv == d) ? 0x80000000u : 0u;
-    return d > tmax ? static_cast<unsigned>(nthr) : pos;   // after every threshold: bin nthr, part of no count
+    const unsigned e = s_fine[fine_of(d)];
+    const unsigned base = e & 0xffu;
+    // first threshold of the bin; when the bin is empty: the first one of a LATER bin, which is > d,
+    // or the +inf padding (s_thr has 256 slots, nthr <= 255) -- so no test of the count is needed
+    const float tv = s_thr[base];
+    unsigned pos = base + (tv <= d ? 1u : 0u);
+    pos |= (e > 0x1ffu || tv == d) ? 0x80000000u : 0u;     // several thresholds in the bin, or a bit-tie
+    return pos;
   };
   // bins with several thresholds, bit-ties: bisection inside the bin + the (distance, index) rule
   auto slow_pos = [&](float d, int g) -> unsigned {
@@ -726,6 +604,19 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
     unsigned pos = fast_pos(d);
     if (pos & 0x80000000u) pos = slow_pos(d, g);
     bump(pos);
+  };
+  auto place8 = [&](const float4& x, const float4& y, int g0, int g1) {
+    const float d[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    unsigned pos[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pos[k] = fast_pos(d[k]);
+    if ((pos[0] | pos[1] | pos[2] | pos[3] | pos[4] | pos[5] | pos[6] | pos[7]) & 0x80000000u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (pos[k] & 0x80000000u) pos[k] = slow_pos(d[k], (k < 4 ? g0 : g1) + (k & 3));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bump(pos[k]);
   };
   auto place4 = [&](const float4& x, int g0) {
     const float d[4] = {x.x, x.y, x.z, x.w};
@@ -769,8 +660,12 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
   for (int k = 0; k < n_full; ++k, v += 2 * kC8Threads) {
     const float4 x = __ldcs(row4 + v), y = __ldcs(row4 + v + kC8Threads);
     const int g0 = head + 4 * v;
-    place4(x, g0);             // (one batch of 8 costs more instructions: the slow-path test fires twice as often)
-    place4(y, g0 + 4 * kC8Threads);
+    if (kC8Batch8) {
+      place8(x, y, g0, g0 + 4 * kC8Threads);
+    } else {
+      place4(x, g0);
+      place4(y, g0 + 4 * kC8Threads);
+    }
     if (++iters == kC8FlushIters) {
       flush();
       iters = 0;
@@ -806,27 +701,16 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
   static_assert(kCmWin == kCmThreads * 8, "scan layout");
   CountRows rows;
   if (rows_) rows = *rows_;
-  // rows with <= 63 finite thresholds: private-histogram kernel; the others: generic windows
-  constexpr int smem = 64 * kCfThreads * 2;
-  static PerDeviceInt configured;
-  DEMO_CHECK_CUDA(ensure_dynamic_smem(configured, count_matrix63_kernel, smem));
-  static const bool all255 = getenv("DEMO_COUNT255_ALL") != nullptr;   // A/B experiments: arithmetic-bin kernel for every row
-  const bool fast = !all255 && G < (1 << 24) - 512;   // u16 private counters: at most G / 256 (+ head / tail) increments per thread
-  if (fast) {
-    count_matrix63_kernel<<<Q, kCfThreads, smem, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
-                                                          thr_val, thr_gidx, counts, rows);
-    DEMO_CHECK_CUDA(cudaGetLastError());
-  }
-  // rows with 64 .. 255 finite thresholds (all rows up to 255 when the u16 kernel is out of range)
-  if (max_cnt > kCfWin || !fast) {
+  // rows with up to 255 finite thresholds
+  {
     // histogram rows: one per slot of the longest row this kernel takes (more resident blocks for short lists)
-    const int top = max_cnt < kC8Bins - 1 ? max_cnt : kC8Bins - 1;
-    const int hist_rows = (top + 1 + 31) / 32 * 32 < 64 ? 64 : (top + 1 + 31) / 32 * 32;   // >= 33 rows: setup scratch
+    const int top = max_cnt < kC8Bins - 1 ? (max_cnt > 0 ? max_cnt : 1) : kC8Bins - 1;
+    const int hist_rows = (top + 1 + 31) / 32 * 32 < 64 ? 64 : (top + 1 + 31) / 32 * 32;   // >= 4 rows: setup scratch
     const int smem8 = hist_rows * kC8Threads;
     static PerDeviceInt configured8;
     DEMO_CHECK_CUDA(ensure_dynamic_smem(configured8, count_matrix255_kernel, kC8Bins * kC8Threads));
     count_matrix255_kernel<<<Q, kC8Threads, smem8, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
-                                                             thr_val, thr_gidx, counts, fast ? 0 : 1, hist_rows, rows);
+                                                             thr_val, thr_gidx, counts, hist_rows, rows);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
   // everything else (longer rows, non-finite thresholds): generic windows
