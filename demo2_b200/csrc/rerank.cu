@@ -151,12 +151,17 @@ topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const fl
   const int pre = kCached ? cols : min(cols, prefix);
   const int pre2 = vec2 ? (pre >> 1) : 0;
   if (vec2) {
+    // minimum in the float domain (fminf skips NaN; + 0.f makes -0 the canonical +0), ONE key at the end
     const float2* src2 = reinterpret_cast<const float2*>(src);
-#pragma unroll 4
+    float fmin_ = INFINITY;
+    bool any = false;
+#pragma unroll 8
     for (int j = t; j < pre2; j += kTopkThreads) {
       const float2 v = __ldg(src2 + j);
-      tmin = min(tmin, min(float_key(v.x + 0.f), float_key(v.y + 0.f)));
+      fmin_ = fminf(fmin_, fminf(v.x + 0.f, v.y + 0.f));
+      any = true;
     }
+    if (any) tmin = min(tmin, float_key(fmin_));
   }
   for (int j = 2 * pre2 + t; j < pre; j += kTopkThreads) {
     const unsigned raw = float_key(__ldg(src + j) + 0.f);
@@ -199,12 +204,19 @@ topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const fl
     }
   };
   if (vec2) {
+    // filter in the float domain: key(x) <= key(b) <=> x <= b for canonical non-NaN values (a NaN
+    // bound only arises when fewer than k entries are not NaN: then every comparison must pass)
     const float2* src2 = reinterpret_cast<const float2*>(src);
-#pragma unroll 4
+    const float bound_f = key_float(bound);
+    const bool all = bound_f != bound_f;
+#pragma unroll 8
     for (int j = t; j < cols2; j += kTopkThreads) {
       const float2 v = __ldg(src2 + j);
-      offer(float_key(v.x + 0.f), 2 * j);
-      offer(float_key(v.y + 0.f), 2 * j + 1);
+      const float a = v.x + 0.f, b = v.y + 0.f;
+      if (all || a <= bound_f || b <= bound_f) {
+        offer(float_key(a), 2 * j);
+        offer(float_key(b), 2 * j + 1);
+      }
     }
   }
   for (int j = 2 * cols2 + t; j < cols; j += kTopkThreads) offer(raw_at(j), j);
