@@ -527,11 +527,17 @@ def other_workloads(dev, peaks):
     from demo2_b200 import metrics, reranking, synth, triplet_loss
     from oracle import reid_oracle as oracle
 
+    spin_a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+    spin_b = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+
     def timed(fn, iters=10, warm=3, busy_s=0.2):
-        # warm-up: at least `warm` calls AND `busy_s` of continuous GPU work -- these workloads take
-        # a millisecond or less, and after the CPU legs (seconds of host-only work) the GPU needs
-        # tens of milliseconds to leave its idle clocks (measured: the first 10 calls after a CPU
-        # leg ran 8-15x slower than the same calls a moment later)
+        # These workloads are a handful of sub-millisecond kernels with a host read per call: too
+        # light a load to pull the GPU out of its idle clocks after a host-side pause (data
+        # generation, the previous leg's CPU work).  Measured: the same 10 calls 0.65 ms each, or
+        # 2 .. 11 ms each right after a pause.  So: ~40 ms of dense GEMM to raise the clocks, then
+        # at least `warm` calls AND `busy_s` of the workload itself, then the timed calls.
+        for _ in range(48):
+            torch.mm(spin_a, spin_b)
         t0 = time.perf_counter()
         n = 0
         while n < warm or time.perf_counter() - t0 < busy_s:

@@ -164,12 +164,13 @@ sqdist_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               const volatile unsigned* flag = sched.pace + j;
               if (*flag < expect) {
                 // Pacing is a performance device, never a correctness dependency: if the others do not
-                // show up within 20 ms (part of the grid not resident yet because another kernel
-                // holds SMs), this worker stops waiting for the rest of the launch.
+                // show up within 3 ms = ten units of the largest problem (part of the grid not resident
+                // because another kernel or another tenant holds SMs), this worker stops waiting for
+                // the rest of the launch.
                 const unsigned long long t0 = globaltimer_ns();
                 while (*flag < expect) {
                   __nanosleep(500);
-                  if (globaltimer_ns() - t0 > 20000000ull) {
+                  if (globaltimer_ns() - t0 > 3000000ull) {
                     paced = false;
                     break;
                   }
