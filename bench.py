@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import argparse
 import builtins
+import gc
 import json
 import os
 import subprocess
@@ -302,6 +303,8 @@ def run_ours(args):
         sampler.start()
     timers = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.collect()
+    gc.disable()           # no interpreter garbage collection (10 .. 100 ms pauses) inside a timed region
     barrier()
     e0.record()
     for _ in range(args.steps):
@@ -310,6 +313,7 @@ def run_ours(args):
         timers.append(t)
     e1.record()
     barrier()
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None
     count_ms_local = float(np.mean([t["count"][0].elapsed_time(t["count"][1]) for t in timers]))
     ms_total, count_ms = max_over_ranks([e0.elapsed_time(e1), count_ms_local])
@@ -343,6 +347,8 @@ def run_ours(args):
     barrier()
     n_e2e = max(3, min(args.steps, 6))
     e2e_timers = []
+    gc.collect()
+    gc.disable()
     e0.record()
     for _ in range(n_e2e):
         t = {}
@@ -350,6 +356,7 @@ def run_ours(args):
         e2e_timers.append(t)
     e1.record()
     barrier()
+    gc.enable()
     e2e_total = e0.elapsed_time(e1)
     same = bool(res2.mAP == res.mAP and np.array_equal(res2.cmc, res.cmc))
 
@@ -531,27 +538,32 @@ def other_workloads(dev, peaks):
     spin_b = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
 
     def timed(fn, iters=10, warm=3, busy_s=0.2):
-        # These workloads are a handful of sub-millisecond kernels with a host read per call: too
-        # light a load to pull the GPU out of its idle clocks after a host-side pause (data
-        # generation, the previous leg's CPU work).  Measured: the same 10 calls 0.65 ms each, or
-        # 2 .. 11 ms each right after a pause.  So: ~40 ms of dense GEMM to raise the clocks, then
-        # at least `warm` calls AND `busy_s` of the workload itself, then the timed calls.
+        # Sub-millisecond workloads: ~40 ms of dense GEMM to raise the clocks after a host-side
+        # pause, at least `warm` calls AND `busy_s` of the workload itself (with the allocation
+        # pattern of the timed loop, see below), no interpreter GC inside the timed calls.  What
+        # used to blow single entries up to 2 .. 11 ms was a cudaMalloc inside the timed loop.
         for _ in range(48):
             torch.mm(spin_a, spin_b)
         t0 = time.perf_counter()
         n = 0
+        out = None
         while n < warm or time.perf_counter() - t0 < busy_s:
-            fn()
-            n += 1
+            out = fn()     # keep the previous result alive during the next call, exactly as the timed loop does:
+            n += 1         # otherwise the first timed call needs a second buffer and pays a cudaMalloc (3 .. 40 ms)
             if n % 4 == 0:
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            out = fn()
-        e1.record()
-        torch.cuda.synchronize()
+        gc.collect()
+        gc.disable()       # a full collection of the interpreter's heap takes 10 .. 100 ms: ten times one of these calls
+        try:
+            e0.record()
+            for _ in range(iters):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+        finally:
+            gc.enable()
         return e0.elapsed_time(e1) / iters, out
 
     hbm = peaks["hbm_gbs"]
@@ -708,7 +720,7 @@ def large_r171(dev, timed):
         e = min(G, s + 131072)
         gf[s:e] = centers[gp_dev[s:e]] + sigma * torch.randn(e - s, d, device=dev, generator=gen)
     plan = metrics.RankPlan(q_pid, g_pid, q_cam, g_cam)
-    ms, r = timed(lambda: metrics.evaluate_features(qf, gf, plan=plan, normalize=True), iters=3, warm=1)
+    ms, r = timed(lambda: metrics.evaluate_features(qf, gf, plan=plan, normalize=True), iters=3, warm=2)
     return {"ms": ms, "queries_per_s": Q / ms * 1e3, "mAP": float(r.mAP), "max_positives_per_query": plan.max_cnt,
             "shape": "20 000 x 1 000 000, d=1536, 5 850 ids",
             "path": "every 256-row query block is flagged: stored slab GEMM + streaming count (one GEMM pass "
