@@ -329,3 +329,18 @@ def test_ddp_evaluator_matches_rank0_evaluation(world, mode):
         assert abs(out[rk][1] - mAP_o) < 1e-12
         np.testing.assert_array_equal(out[rk][3], first_o)
     assert all(out[0][1] == out[rk][1] for rk in range(world))
+
+
+def test_streamed_evaluation_host_logic():
+    """Pure host logic of the streamed evaluation: query-block boundaries (multiples of 1024 rows,
+    first 0, last Q, strictly increasing) and the slab size rule (at least six slabs for small
+    shards, 8 192 .. 131 072 rows, an explicit value wins)."""
+    from demo2_b200.parallel import ShardedEvaluator as SE
+    for Q, groups in [(20000, 4), (2600, 4), (2048, 2), (1500, 4), (4200, 3), (1024, 8)]:
+        qb = SE._query_bounds(Q, groups)
+        assert qb[0] == 0 and qb[-1] == Q and all(b > a for a, b in zip(qb, qb[1:]))
+        assert all(b % 1024 == 0 for b in qb[1:-1]) and len(qb) - 1 <= max(1, min(groups, Q // 1024))
+    assert SE._query_bounds(20000, 4) == [0, 5120, 10240, 15360, 20000]
+    assert SE._slab_rows(None, 669000) == 111616 and SE._slab_rows(None, 84000) == 14080
+    assert SE._slab_rows(None, 100) == 8192 and SE._slab_rows(None, 10 ** 7) == 131072
+    assert SE._slab_rows(500, 10 ** 6) == 500
