@@ -505,7 +505,7 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
                        const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int hist_rows,
                        CountRows rows) {
   extern __shared__ __align__(16) unsigned char s_hist8[];   // [hist_rows][256] u8, column = thread (>= 4 rows: scratch)
-  __shared__ float s_thr[kC8Bins];                           // padded with +inf
+  __shared__ float s_thr[kC8Bins];                           // padded with NaN (never <= or == an element, +inf included)
   __shared__ int s_tg[kC8Bins];
   __shared__ unsigned short s_fine[kC8Fine + 2];             // first threshold of the bin | count << 8
   __shared__ unsigned s_tot[kC8Bins];
@@ -516,7 +516,7 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
   if (nthr <= 0 || nthr > kC8Bins - 1 || nthr >= hist_rows) return;   // longer rows: count_matrix_kernel
   const int tbase = thr_ofs[i];
   if (!isfinite(__ldg(thr_val + tbase + nthr - 1))) return;
-  s_thr[t] = t < nthr ? __ldg(thr_val + tbase + t) : INFINITY;
+  s_thr[t] = t < nthr ? __ldg(thr_val + tbase + t) : __int_as_float(0x7fc00000);
   s_tg[t] = t < nthr ? __ldg(thr_gidx + tbase + t) : -1;
   s_tot[t] = 0u;
   __syncthreads();
@@ -572,7 +572,8 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
     const unsigned e = s_fine[fine_of(d)];
     const unsigned base = e & 0xffu;
     // first threshold of the bin; when the bin is empty: the first one of a LATER bin, which is > d,
-    // or the +inf padding (s_thr has 256 slots, nthr <= 255) -- so no test of the count is needed
+    // or the NaN padding (s_thr has 256 slots, nthr <= 255; an element may be +inf) -- so no test of
+    // the count is needed and pos never exceeds nthr
     const float tv = s_thr[base];
     unsigned pos = base + (tv <= d ? 1u : 0u);
     pos |= (e > 0x1ffu || tv == d) ? 0x80000000u : 0u;     // several thresholds in the bin, or a bit-tie

@@ -134,10 +134,14 @@ def test_eval_func_rows_with_64_to_255_positives(M, G, nid, levels):
     if levels:
         dist = np.round(dist * levels).astype(np.float32) / np.float32(levels)
     qp, gp = rng.integers(0, nid, Q), rng.integers(0, nid, G)
+    gp[::97] = 10 ** 6                          # columns of an identity nobody asks for ...
+    dist[:, ::97] = np.inf                      # ... masked: after every threshold, part of no count
+    gp[1::89] = 10 ** 6 + 1
+    dist[::5, 1::89] = -np.inf                  # and before every threshold
     qc, gc = rng.integers(0, 6, Q), rng.integers(0, 6, G)
     res = M.evaluate_matrix(dist, qp, gp, qc, gc)
     ofs, idx, r, c = oracle.rank_counts(dist, qp, gp, qc, gc)
-    per_id = np.bincount(gp, minlength=nid)
+    per_id = np.bincount(gp[gp < nid], minlength=nid)
     if nid == 11:     # ~250 valid positives per query: rows on both sides of the 255-threshold limit of the binning kernel
         n_thr = np.diff(ofs)
         assert int(n_thr.min()) <= 255 < int(n_thr.max())
