@@ -213,7 +213,7 @@ int demo_rerank_shard_jaccard(int N, int Q, int d, int k1, int k2, double lambda
   if (nq_local < 0) nq_local = 0;
   DEMO_REQUIRE(nq_local == 0 || (out_rows && ldo >= N - Q), "rerank shard: bad output");
   const int f_cap = k2 != 1 ? rerank_capq(N, k1, k2) : rerank_cap(k1);
-  return launch_jaccard_rows(w.E, e_pitch(N), w.rowmax, N, Q, lambda_value, row0, nq_local, f_idx,
+  return launch_jaccard_rows(w.E, e_pitch(N), w.rowmax, N, Q, k1, k2, lambda_value, row0, nq_local, f_idx,
                              static_cast<const __half*>(f_val), f_cnt, f_cap, w.r, out_rows, ldo,
                              static_cast<cudaStream_t>(stream_));
 }

@@ -445,6 +445,7 @@ krecip_kernel(const float* __restrict__ E, long long lde, const float* __restric
 // local query expansion: V_qe[i] = fp16(mean_m V[rank[i][m]]), m < k2 (one block per row)
 // ---------------------------------------------------------------------------------------
 constexpr int kQeThreads = 128;
+constexpr int kQeAcc = 2048;    // output slots accumulated per pass of the expansion kernel
 
 // The union of the k2 neighbour rows is built as a bitmap (= sorted unique columns); the weights are
 // then SCATTERED into their output slot, found by a rank query on the bitmap (per-word prefix +
@@ -459,8 +460,10 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
   const int words = ceil_div(N, 32);
   unsigned* bm = s_dyn;
   unsigned* wp = s_dyn + words;                                   // [words] set bits before each word
-  int* s_list = reinterpret_cast<int*>(s_dyn + 2 * words);        // [capq]
-  float* s_acc = reinterpret_cast<float*>(s_list + capq);         // [capq]
+  // fp32 accumulators for kQeAcc output slots at a time (the union of k2 rows has a few hundred
+  // entries; its worst-case bound capq = min(N, k2 * cap) used to size TWO shared arrays -- 82 KB
+  // at k1 = 50, k2 = 15, N = 10 290, two blocks per SM); the column list goes straight to q_idx
+  float* s_acc = reinterpret_cast<float*>(s_dyn + 2 * words);     // [kQeAcc]
   __shared__ unsigned s_scan[kQeThreads + 1];
   __shared__ int s_nb[64], s_cnt[64];
   const int i = blockIdx.x + row0, t = threadIdx.x;
@@ -477,52 +480,74 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
       if (__half2float(v_val[(long long)r * cap + p]) != 0.f) bm_set(bm, v_idx[(long long)r * cap + p]);
   }
   __syncthreads();
-  const int n = bm_enumerate(bm, words, s_list, capq, s_scan, wp);
+  const int n = bm_enumerate(bm, words, q_idx + (long long)i * capq, capq, s_scan, wp);
   const int nn = min(n, capq);
-  for (int p = t; p < nn; p += kQeThreads) s_acc[p] = 0.f;
-  __syncthreads();
-  for (int m = 0; m < k2; ++m) {  // sequential float32 sum in neighbour order (np.mean over fp16 rows)
-    const int r = s_nb[m];
-    const int cnt = s_cnt[m];
-    for (int p = t; p < cnt; p += kQeThreads) {
-      const float v = __half2float(v_val[(long long)r * cap + p]);
-      if (v == 0.f) continue;
-      const int c = v_idx[(long long)r * cap + p];
-      const unsigned pos = wp[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u));
-      if (pos < static_cast<unsigned>(nn)) s_acc[pos] += v;   // columns of one row are distinct: no conflict
-    }
-    __syncthreads();
-  }
   const float k2f = static_cast<float>(k2);
-  for (int p = t; p < nn; p += kQeThreads) {
-    q_idx[(long long)i * capq + p] = s_list[p];
-    q_val[(long long)i * capq + p] = __float2half_rn(s_acc[p] / k2f);
+  for (int c0 = 0; c0 < nn; c0 += kQeAcc) {          // one pass unless the union is unusually large
+    const int cn = min(kQeAcc, nn - c0);
+    for (int p = t; p < cn; p += kQeThreads) s_acc[p] = 0.f;
+    __syncthreads();
+    for (int m = 0; m < k2; ++m) {  // sequential float32 sum in neighbour order (np.mean over fp16 rows)
+      const int r = s_nb[m];
+      const int cnt = s_cnt[m];
+      for (int p = t; p < cnt; p += kQeThreads) {
+        const float v = __half2float(v_val[(long long)r * cap + p]);
+        if (v == 0.f) continue;
+        const int c = v_idx[(long long)r * cap + p];
+        const unsigned pos = wp[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u)) - static_cast<unsigned>(c0);
+        if (pos < static_cast<unsigned>(cn)) s_acc[pos] += v;   // columns of one row are distinct: no conflict
+      }
+      __syncthreads();
+    }
+    for (int p = t; p < cn; p += kQeThreads)
+      q_val[(long long)i * capq + c0 + p] = __float2half_rn(s_acc[p] / k2f);
+    __syncthreads();
   }
   if (t == 0) q_cnt[i] = nn;
 }
 
 // ---------------------------------------------------------------------------------------
-// inverted index (column lists; order inside a column is irrelevant)
+// inverted index of the GALLERY rows of the final V (temp_min of a query row is only read at the
+// gallery columns, :94-95; the query rows were 17 % of the entries at RGBNT100 scale and half of
+// them at RGBNT201 scale).  An entry is ONE word -- gallery row in the upper half, fp16 weight in
+// the lower half -- or, for galleries of more than 65 536 rows, a (row, weight) pair of words.
+// The order inside a column list is irrelevant: its rows are distinct.
 // ---------------------------------------------------------------------------------------
+struct JcWide { unsigned row, val; };
+__device__ __forceinline__ unsigned jc_make(unsigned, int g, __half v) {
+  return (static_cast<unsigned>(g) << 16) | __half_as_ushort(v);
+}
+__device__ __forceinline__ JcWide jc_make(JcWide, int g, __half v) {
+  return JcWide{static_cast<unsigned>(g), __half_as_ushort(v)};
+}
+__device__ __forceinline__ unsigned jc_row(unsigned e) { return e >> 16; }
+__device__ __forceinline__ __half jc_val(unsigned e) { return __ushort_as_half(static_cast<unsigned short>(e & 0xffffu)); }
+__device__ __forceinline__ unsigned jc_row(JcWide e) { return e.row; }
+__device__ __forceinline__ __half jc_val(JcWide e) { return __ushort_as_half(static_cast<unsigned short>(e.val)); }
+__device__ __forceinline__ unsigned jc_load(const unsigned* p) { return __ldg(p); }
+__device__ __forceinline__ JcWide jc_load(const JcWide* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  return JcWide{u.x, u.y};
+}
+
 __global__ void inv_count_kernel(const int* __restrict__ idx, const __half* __restrict__ val, const int* __restrict__ cnt,
-                                 int cap, int N, int* __restrict__ col_cnt) {
-  const int i = blockIdx.x;
+                                 int cap, int Q, int* __restrict__ col_cnt) {
+  const int i = blockIdx.x + Q;
   const int c = cnt[i];
   for (int p = threadIdx.x; p < c; p += blockDim.x)
     if (__half2float(val[(long long)i * cap + p]) != 0.f) atomicAdd(&col_cnt[idx[(long long)i * cap + p]], 1);
 }
+template <typename Ent>
 __global__ void inv_fill_kernel(const int* __restrict__ idx, const __half* __restrict__ val, const int* __restrict__ cnt,
-                                int cap, int N, const int* __restrict__ inv_ofs, int* __restrict__ cursor,
-                                int* __restrict__ inv_row, __half* __restrict__ inv_val) {
-  const int i = blockIdx.x;
+                                int cap, int Q, const int* __restrict__ inv_ofs, int* __restrict__ cursor,
+                                Ent* __restrict__ inv_ent) {
+  const int g = blockIdx.x, i = g + Q;
   const int c = cnt[i];
   for (int p = threadIdx.x; p < c; p += blockDim.x) {
     const __half v = val[(long long)i * cap + p];
     if (__half2float(v) != 0.f) {
       const int col = idx[(long long)i * cap + p];
-      const int slot = inv_ofs[col] + atomicAdd(&cursor[col], 1);
-      inv_row[slot] = i;
-      inv_val[slot] = v;
+      inv_ent[inv_ofs[col] + atomicAdd(&cursor[col], 1)] = jc_make(Ent{}, g, v);
     }
   }
 }
@@ -531,67 +556,81 @@ __global__ void inv_fill_kernel(const int* __restrict__ idx, const __half* __res
 // Jaccard distance + blend (one block per query row).
 // temp_min[t] receives, for ascending columns j of V[i], fp16(temp_min[t] + min(V[i,j], V[t,j]))
 // (:89-93), so the columns are applied one after another with a block barrier in between (a row
-// may be hit by different threads in consecutive columns).  What used to make a column cost a
-// microsecond were three dependent global loads (V[i] entry -> inverted-list range -> entries):
-// the column metadata is now staged in shared memory per chunk and the entries of 8 columns are
-// fetched together before they are applied in order.
+// may be hit by different threads in consecutive columns).  The column metadata is staged in
+// shared memory per chunk and the entries of 8 columns (kAhead per thread and column: 1 for lists
+// of up to 256 gallery rows, 3 for the ~500-entry lists of k1 = 50 / k2 = 15) are fetched
+// together before they are applied in order.
+// Measured alternative (round 2, reverted): every warp owns the rows of one residue class and
+// walks the columns alone with __syncwarp only -- 1.10 ms instead of 1.07 ms at k1 = 50 / k2 = 15
+// and 0.24 instead of 0.115 ms at 20 / 6: the kernel is bound by shared-memory wavefronts (a
+// read-modify-write of 32 random fp16 slots costs ~7 of them), not by the barriers, and the
+// per-class lists fill the lanes worse.
 // ---------------------------------------------------------------------------------------
 constexpr int kJcThreads = 256;
 constexpr int kJcChunk = 512;   // columns staged per round
 constexpr int kJcGroup = 8;     // columns whose entries are fetched together
 
-__global__ void __launch_bounds__(kJcThreads)
+template <typename Ent, int kAhead>
+__global__ void __launch_bounds__(kJcThreads, kAhead == 1 ? 8 : 4)
 jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ rowmax, int N, int Q,
                const int* __restrict__ idx, const __half* __restrict__ val, const int* __restrict__ cnt, int cap,
-               const int* __restrict__ inv_ofs, const int* __restrict__ inv_row, const __half* __restrict__ inv_val,
+               const int* __restrict__ inv_ofs, const Ent* __restrict__ inv_ent,
                float one_minus_lambda_h, float lambda_f, __half* __restrict__ scratch, float* __restrict__ out,
                long long ldo, int row0) {
   extern __shared__ __half s_tmin[];
-  __shared__ int s_beg[kJcChunk], s_end[kJcChunk];
-  __shared__ float s_v[kJcChunk];
+  __shared__ int s_beg[kJcChunk], s_len[kJcChunk];
+  __shared__ __half s_v[kJcChunk];
   const int li = blockIdx.x, i = li + row0, t = threadIdx.x;   // E / rowmax / scratch / out: local rows
-  __half* tmin = scratch ? scratch + (long long)li * N : s_tmin;
-  for (int j = t; j < N; j += kJcThreads) tmin[j] = __float2half_rn(0.f);
+  const int G = N - Q;
+  __half* tmin = scratch ? scratch + (long long)li * G : s_tmin;   // gallery rows only
+  for (int j = t; j < G; j += kJcThreads) tmin[j] = __float2half_rn(0.f);
   const int c = cnt[i];
   for (int p0 = 0; p0 < c; p0 += kJcChunk) {
     __syncthreads();  // tmin initialised / previous chunk consumed
     const int np = min(kJcChunk, c - p0);
     for (int p = t; p < np; p += kJcThreads) {
       const int col = idx[(long long)i * cap + p0 + p];
-      s_v[p] = __half2float(val[(long long)i * cap + p0 + p]);   // 0 -> column skipped (V != 0 test, :88)
-      s_beg[p] = inv_ofs[col];
-      s_end[p] = inv_ofs[col + 1];
+      const __half v = val[(long long)i * cap + p0 + p];
+      const int beg = inv_ofs[col];
+      s_v[p] = v;
+      s_beg[p] = beg;
+      s_len[p] = __half2float(v) != 0.f ? inv_ofs[col + 1] - beg : 0;   // V[i, col] == 0 -> column skipped (:88)
     }
     __syncthreads();
-    // columns in groups of kJcGroup: every thread first fetches its entry of each column of the
+    // columns in groups of kJcGroup: every thread first fetches its entries of each column of the
     // group (independent loads, one L2 latency for the whole group), then the columns are applied
     // in order
     for (int p8 = 0; p8 < np; p8 += kJcGroup) {
-      int er[kJcGroup];
-      __half ev[kJcGroup];
+      Ent ent[kJcGroup][kAhead];
 #pragma unroll
       for (int u = 0; u < kJcGroup; ++u) {
         const int p = p8 + u;
-        er[u] = -1;
-        ev[u] = __float2half_rn(0.f);
-        if (p < np && s_beg[p] + t < s_end[p]) {
-          er[u] = __ldg(inv_row + s_beg[p] + t);
-          ev[u] = inv_val[s_beg[p] + t];
-        }
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k)
+          if (p < np && t + k * kJcThreads < s_len[p]) ent[u][k] = jc_load(inv_ent + s_beg[p] + t + k * kJcThreads);
       }
 #pragma unroll
       for (int u = 0; u < kJcGroup; ++u) {  // ascending column order (:89-93)
         const int p = p8 + u;
         if (p >= np) break;
-        const float vij = s_v[p];
-        if (vij == 0.f) continue;  // block-uniform
+        const int len = s_len[p];
+        if (len == 0) continue;  // block-uniform
         // native half min / add (IEEE round-to-nearest): identical to numpy's "compute in float32,
         // round once" for + of two halfs; 3 instructions instead of 8
-        const __half vh = __float2half_rn(vij);   // exact: vij was a half
-        if (er[u] >= 0) tmin[er[u]] = __hadd(tmin[er[u]], __hmin(vh, ev[u]));
-        for (int q = s_beg[p] + kJcThreads + t; q < s_end[p]; q += kJcThreads) {  // lists longer than one entry per thread
-          const int r = __ldg(inv_row + q);
-          tmin[r] = __hadd(tmin[r], __hmin(vh, inv_val[q]));
+        const __half vh = s_v[p];
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k)
+          if (t + k * kJcThreads < len) {
+            const unsigned r = jc_row(ent[u][k]);
+            tmin[r] = __hadd(tmin[r], __hmin(vh, jc_val(ent[u][k])));
+          }
+        if (len > kAhead * kJcThreads) {     // longer lists
+          const Ent* lst = inv_ent + s_beg[p];
+          for (int q = kAhead * kJcThreads + t; q < len; q += kJcThreads) {
+            const Ent en = jc_load(lst + q);
+            const unsigned r = jc_row(en);
+            tmin[r] = __hadd(tmin[r], __hmin(vh, jc_val(en)));
+          }
         }
         __syncthreads();
       }
@@ -601,7 +640,6 @@ jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restri
   const __half one = __float2half_rn(1.f), two = __float2half_rn(2.f);
   const __half w = __float2half_rn(one_minus_lambda_h);
   const float div = rowmax[li];
-  const int G = N - Q;
   // 8 independent row loads in flight per thread: with 64 KB of temp_min per block only three blocks
   // fit an SM, so the memory-level parallelism has to come from the thread
   const float* erow = E + (long long)li * lde + Q;
@@ -617,7 +655,7 @@ jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restri
     for (int u = 0; u < 8; ++u) {
       const int g = g0 + u * kJcThreads;
       if (g >= G) break;
-      const __half tm = tmin[Q + g];
+      const __half tm = tmin[g];
       const __half jac = np_hsub(one, np_hdiv(tm, np_hsub(two, tm)));           // 1 - tmin / (2 - tmin)
       const float od = e[u] / div;
       __stcs(orow + g, __fadd_rn(__half2float(np_hmul(jac, w)), __fmul_rn(od, lambda_f)));  // (:95), no FMA contraction
@@ -687,6 +725,66 @@ int rerank_capq(int N, int k1, int k2) {
   return static_cast<int>(c < N ? c : N);
 }
 
+constexpr size_t kJcMaxSmemTmin = 200 * 1024;
+constexpr int kJcPackedRows = 65536;   // gallery rows a one-word inverted-list entry can address
+
+template <typename Ent, int kAhead>
+static int launch_jaccard_t(int nq, size_t smem, cudaStream_t stream, const float* E, long long lde, const float* rowmax,
+                            int N, int Q, const int* f_idx, const __half* f_val, const int* f_cnt, int f_cap,
+                            const RerankWs& w, float oml, float lambda_f, float* out, long long ldo, int row0) {
+  auto kern = jaccard_kernel<Ent, kAhead>;
+  DEMO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kJcMaxSmemTmin)));
+  kern<<<nq, kJcThreads, smem, stream>>>(E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w.inv_ofs,
+                                         static_cast<const Ent*>(w.inv_ent), oml, lambda_f, w.tmin_scratch, out, ldo, row0);
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  return DEMO_OK;
+}
+
+// inverted index of the gallery rows of the final V + Jaccard / blend rows of the queries
+// [row0, row0 + nq): shared by the one-GPU and the row-sharded flow
+static int launch_index_and_jaccard(const float* E, long long lde, const float* rowmax, int N, int Q, int k1, int k2,
+                                    double lambda_value, int row0, int nq, const int* f_idx, const __half* f_val,
+                                    const int* f_cnt, int f_cap, const RerankWs& w, float* out, long long ldo,
+                                    cudaStream_t stream) {
+  const int G = N - Q;
+  DEMO_REQUIRE(G >= 1, "re_ranking: empty gallery");
+  const bool packed = G <= kJcPackedRows;
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
+  DEMO_CHECK_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int) * (N + 1), stream));
+  inv_count_kernel<<<G, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, Q, w.col_cnt);
+  size_t tmp = w.cub_bytes;
+  DEMO_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.col_cnt, w.inv_ofs, N + 1, stream));
+  if (packed)
+    inv_fill_kernel<unsigned><<<G, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, Q, w.inv_ofs, w.cursor,
+                                                     static_cast<unsigned*>(w.inv_ent));
+  else
+    inv_fill_kernel<JcWide><<<G, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, Q, w.inv_ofs, w.cursor,
+                                                   static_cast<JcWide*>(w.inv_ent));
+  DEMO_CHECK_CUDA(cudaGetLastError());
+  if (nq <= 0) return DEMO_OK;
+  // (1 - lambda) is a Python float: numpy multiplies the fp16 array by fp16(1 - lambda)
+  const float oml = __half2float(__double2half(1.0 - lambda_value)), lam = static_cast<float>(lambda_value);
+  const size_t smem = w.tmin_scratch ? 0 : static_cast<size_t>(G) * 2;
+  // Entries per column list ~ non-zeros per row of the final V x (gallery share of the rows):
+  // ~0.8 k1 k2 after the expansion (measured 96 at 20 / 6 and 583 at 50 / 15 on RGBNT100-like
+  // data), ~k1 without it.  The estimate only picks the prefetch depth; any length is handled.
+  const double est = (k2 > 1 ? 0.8 * k1 * k2 : 1.0 * k1) * G / N;
+  static const int force = getenv("DEMO_JC_AHEAD") ? atoi(getenv("DEMO_JC_AHEAD")) : 0;   // A/B experiments
+  // measured at 50 / 15 (lists of ~480 gallery rows): depth 2 0.77 ms, depth 3 0.80 ms, depth 1 (round 1) 1.07 ms
+  const int ahead = force ? force : est <= 0.8 * kJcThreads ? 1 : est <= 3.0 * kJcThreads ? 2 : 3;
+#define DEMO_JC(ENT, A) \
+  return launch_jaccard_t<ENT, A>(nq, smem, stream, E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w, oml, lam, out, ldo, row0)
+  if (packed) {
+    if (ahead == 1) DEMO_JC(unsigned, 1);
+    if (ahead == 2) DEMO_JC(unsigned, 2);
+    DEMO_JC(unsigned, 3);
+  }
+  if (ahead == 1) DEMO_JC(JcWide, 1);
+  if (ahead == 2) DEMO_JC(JcWide, 2);
+  DEMO_JC(JcWide, 3);
+#undef DEMO_JC
+}
+
 size_t rerank_carve(Carver& c, int N, int Q, int k1, int k2, RerankWs* w) {
   RerankWs t;
   const size_t n = N > 0 ? N : 1;
@@ -702,21 +800,21 @@ size_t rerank_carve(Carver& c, int N, int Q, int k1, int k2, RerankWs* w) {
   t.q_idx = c.take<int>(n * t.capq);
   t.q_val = c.take<__half>(n * t.capq);
   t.q_cnt = c.take<int>(n);
+  const size_t g = N > Q && Q > 0 ? N - Q : n;   // gallery rows: the only ones in the inverted index
   t.col_cnt = c.take<int>(n + 1);
   t.inv_ofs = c.take<int>(n + 1);
   t.cursor = c.take<int>(n + 1);
-  t.inv_row = c.take<int>(n * t.capq);
-  t.inv_val = c.take<__half>(n * t.capq);
+  t.inv_ent = c.take<unsigned>(g * t.capq * (g <= static_cast<size_t>(kJcPackedRows) ? 1 : 2));
   size_t tmp = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp, t.col_cnt, t.inv_ofs, N + 1);
   t.cub_bytes = tmp + 256;
   t.cub_tmp = c.take<char>(t.cub_bytes);
   t.tmin_scratch = nullptr;
   t.tmin_bytes = 0;
-  if (static_cast<size_t>(N) * 2 > 200 * 1024) {  // temp_min does not fit shared memory
+  if (g * 2 > kJcMaxSmemTmin) {  // temp_min (gallery rows) does not fit shared memory
     const size_t q = Q > 0 ? Q : 1;
-    t.tmin_bytes = q * n * 2;
-    t.tmin_scratch = c.take<__half>(q * n);
+    t.tmin_bytes = q * g * 2;
+    t.tmin_scratch = c.take<__half>(q * g);
   }
   if (w) *w = t;
   return c.off;
@@ -749,23 +847,7 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
     f_cnt = w.q_cnt;
     f_cap = w.capq;
   }
-  DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
-  DEMO_CHECK_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int) * (N + 1), stream));
-  inv_count_kernel<<<N, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, N, w.col_cnt);
-  size_t tmp = w.cub_bytes;
-  DEMO_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.col_cnt, w.inv_ofs, N + 1, stream));
-  inv_fill_kernel<<<N, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, N, w.inv_ofs, w.cursor, w.inv_row, w.inv_val);
-  DEMO_CHECK_CUDA(cudaGetLastError());
-  {
-    // (1 - lambda) is a Python float: numpy multiplies the fp16 array by fp16(1 - lambda)
-    const float oml = __half2float(__double2half(1.0 - lambda_value));
-    const size_t smem = w.tmin_scratch ? 0 : static_cast<size_t>(N) * 2;
-    DEMO_CHECK_CUDA(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    jaccard_kernel<<<Q, kJcThreads, smem, stream>>>(E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w.inv_ofs, w.inv_row,
-                                                    w.inv_val, oml, static_cast<float>(lambda_value), w.tmin_scratch, out,
-                                                    ldo, 0);
-    DEMO_CHECK_CUDA(cudaGetLastError());
-  }
+  DEMO_TRY(launch_index_and_jaccard(E, lde, rowmax, N, Q, k1, k2, lambda_value, 0, Q, f_idx, f_val, f_cnt, f_cap, w, out, ldo, stream));
   return DEMO_OK;
 }
 
@@ -799,8 +881,8 @@ int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int
   DEMO_REQUIRE(k2 >= 2 && k2 <= 64 && k2 <= N, "re_ranking: expansion needs 2 <= k2 <= min(N, 64) (k2=%d)", k2);
   if (nrows <= 0) return DEMO_OK;
   const int K = rerank_k(k1, k2), cap = rerank_cap(k1), capq = rerank_capq(N, k1, k2), words = ceil_div(N, 32);
-  const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(capq) * 8;
-  DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d / k2=%d too large for the expansion kernel", N, k2);
+  const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(kQeAcc) * 4;
+  DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d too large for the expansion kernel", N);
   DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   expand_kernel<<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx, q_val,
                                                      q_cnt, row0);
@@ -808,27 +890,13 @@ int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int
   return DEMO_OK;
 }
 
-// Inverted index over ALL N rows of the (gathered) final V, then the Jaccard / blend rows of the
-// local queries [row0, row0 + nq_local), row0 + nq_local <= Q.
-int launch_jaccard_rows(const float* E, long long lde, const float* rowmax, int N, int Q, double lambda_value,
-                        int row0, int nq_local, const int* f_idx, const __half* f_val, const int* f_cnt, int f_cap,
+// Inverted index over the gallery rows of the (gathered) final V, then the Jaccard / blend rows of
+// the local queries [row0, row0 + nq_local), row0 + nq_local <= Q.
+int launch_jaccard_rows(const float* E, long long lde, const float* rowmax, int N, int Q, int k1, int k2,
+                        double lambda_value, int row0, int nq_local, const int* f_idx, const __half* f_val, const int* f_cnt, int f_cap,
                         const RerankWs& w, float* out, long long ldo, cudaStream_t stream) {
-  DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
-  DEMO_CHECK_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int) * (N + 1), stream));
-  inv_count_kernel<<<N, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, N, w.col_cnt);
-  size_t tmp = w.cub_bytes;
-  DEMO_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.col_cnt, w.inv_ofs, N + 1, stream));
-  inv_fill_kernel<<<N, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, N, w.inv_ofs, w.cursor, w.inv_row, w.inv_val);
-  DEMO_CHECK_CUDA(cudaGetLastError());
-  if (nq_local <= 0) return DEMO_OK;
-  const float oml = __half2float(__double2half(1.0 - lambda_value));
-  const size_t smem = w.tmin_scratch ? 0 : static_cast<size_t>(N) * 2;
-  DEMO_CHECK_CUDA(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  jaccard_kernel<<<nq_local, kJcThreads, smem, stream>>>(E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w.inv_ofs,
-                                                         w.inv_row, w.inv_val, oml, static_cast<float>(lambda_value),
-                                                         w.tmin_scratch, out, ldo, row0);
-  DEMO_CHECK_CUDA(cudaGetLastError());
-  return DEMO_OK;
+  return launch_index_and_jaccard(E, lde, rowmax, N, Q, k1, k2, lambda_value, row0, nq_local, f_idx, f_val, f_cnt, f_cap, w, out,
+                                  ldo, stream);
 }
 
 }  // namespace demo

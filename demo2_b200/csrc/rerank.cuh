@@ -19,11 +19,11 @@ struct RerankWs {
   int* col_cnt = nullptr;    // [N+1]
   int* inv_ofs = nullptr;    // [N+1]
   int* cursor = nullptr;     // [N+1]
-  int* inv_row = nullptr;    // [N*capq]
-  __half* inv_val = nullptr;
+  void* inv_ent = nullptr;   // [(N-Q)*capq] inverted-list entries of the gallery rows: (row - Q) << 16 | fp16 weight
+                             // in one word, or two words (row - Q, weight) for more than 65 536 gallery rows
   void* cub_tmp = nullptr;
   size_t cub_bytes = 0;
-  __half* tmin_scratch = nullptr;  // [Q][N] only when N*2 bytes exceed shared memory
+  __half* tmin_scratch = nullptr;  // [Q][N-Q] only when (N-Q)*2 bytes exceed shared memory
   size_t tmin_bytes = 0;
 };
 
@@ -48,7 +48,7 @@ int launch_krecip_rows(const float* E, long long lde, const float* rowmax, const
 int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int nrows, const int* v_idx,
                        const __half* v_val, const int* v_cnt, int* q_idx, __half* q_val, int* q_cnt,
                        cudaStream_t stream);
-int launch_jaccard_rows(const float* E, long long lde, const float* rowmax, int N, int Q, double lambda_value,
+int launch_jaccard_rows(const float* E, long long lde, const float* rowmax, int N, int Q, int k1, int k2, double lambda_value,
                         int row0, int nq_local, const int* f_idx, const __half* f_val, const int* f_cnt, int f_cap,
                         const RerankWs& w, float* out, long long ldo, cudaStream_t stream);
 

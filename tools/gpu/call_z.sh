@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests/test_gpu_rerank.py tests/test_gpu_sharded.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/r2z_pytest.log
+cat gpurun_out/r2z_pytest.log
+for jc in 0 2; do
+export DEMO_JC_AHEAD=$jc
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
+  --log-file gpurun_out/launches_rerank5015_r2z$jc.csv python tools/profile_rerank_50_15.py > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
+  --log-file gpurun_out/launches_rerank_r2z$jc.csv python tools/profile_rerank.py > /dev/null 2>&1
+done
