@@ -117,13 +117,40 @@ __device__ void bitonic_sort_u64(unsigned long long* s, int n2) {
   }
 }
 
+// Streams nvec vectors of a row through f(vector, vector index): kBatch independent loads per thread
+// are issued before the first one is consumed.  (Round 2: `#pragma unroll 8` over float2 left a
+// remainder of single dependent loads -- a 10 290-column row cost ~12 DRAM latencies per block,
+// ncu: 19 of 30 stall cycles per issue on the long scoreboard at 95 % occupancy.)
+template <typename Vec, int kBatch, typename F>
+__device__ __forceinline__ void stream_row(const float* __restrict__ src, int nvec, int t, F&& f) {
+  const Vec* s = reinterpret_cast<const Vec*>(src);
+  for (int base = 0; base < nvec; base += kTopkThreads * kBatch) {
+    Vec v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int j = base + u * kTopkThreads + t;
+      if (j < nvec) v[u] = __ldg(s + j);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int j = base + u * kTopkThreads + t;
+      if (j < nvec) f(v[u], j);
+    }
+  }
+}
+
 // Fast path: the k-th smallest of the per-thread (or per-4-thread) minima is an upper bound T
 // of the k-th smallest entry of the row; the few entries <= T are collected and ranked by
 // (key, index).  Selection runs on the raw entries; the division by row_div (monotone) is
 // applied to the candidates only, after widening T over the entries whose quotient ties with
 // T's.  Fallback (more than kTopkCap candidates, i.e. massive ties): 4 x 8-bit radix select.
+// Measured and dropped (round 2): the whole row in registers (one batch of up to 12 independent
+// 16-byte loads per thread, bound from the whole row, filter from the registers, no second pass):
+// 0.163 instead of 0.107 ms for 10 290 x 10 290 at k = 21 -- 4 resident blocks per SM instead of 6
+// hide the selection / ranking phases worse than the saved L2 pass returns.  Same for a bound from
+// a 4096-entry prefix on these rows (0.119 ms: more candidates to rank).
 template <bool kCached>
-__global__ void __launch_bounds__(kTopkThreads)
+__global__ void __launch_bounds__(kTopkThreads, kCached ? 8 : 6)
 topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const float* __restrict__ row_div, int k,
                  int* __restrict__ idx_out, float* __restrict__ val_out, int prefix) {
   extern __shared__ unsigned s_dyn[];
@@ -142,25 +169,28 @@ topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const fl
   };
   auto key_at = [&](int j) -> unsigned { return final_key(raw_at(j)); };
   unsigned tmin = 0xFFFFFFFFu;
-  // 8-byte vector loads when the row allows it (row start 8-byte aligned)
-  const bool vec2 = !kCached && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
-  const int cols2 = vec2 ? (cols >> 1) : 0;
+  // 16- or 8-byte vector loads when the row start allows it
+  const int vec = kCached ? 1 : ((reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? 4 : (reinterpret_cast<uintptr_t>(src) & 7u) == 0 ? 2 : 1);
+  const int cols2 = vec == 4 ? (cols >> 2) * 2 : vec == 2 ? (cols >> 1) : 0;   // float2 units covered by vector loads
   // The bound only needs a subset of the row (the k-th smallest of ANY >= k entries bounds the
-  // k-th smallest of all): long un-cached rows derive it from a prefix, so that most of the row is
+  // k-th smallest of all): un-cached rows derive it from a prefix, so that most of the row is
   // read from HBM once (the filter pass) instead of twice.
   const int pre = kCached ? cols : min(cols, prefix);
-  const int pre2 = vec2 ? (pre >> 1) : 0;
-  if (vec2) {
+  const int pre2 = vec == 4 ? (pre >> 2) * 2 : vec == 2 ? (pre >> 1) : 0;
+  if (vec > 1) {
     // minimum in the float domain (fminf skips NaN; + 0.f makes -0 the canonical +0), ONE key at the end
-    const float2* src2 = reinterpret_cast<const float2*>(src);
     float fmin_ = INFINITY;
     bool any = false;
-#pragma unroll 8
-    for (int j = t; j < pre2; j += kTopkThreads) {
-      const float2 v = __ldg(src2 + j);
-      fmin_ = fminf(fmin_, fminf(v.x + 0.f, v.y + 0.f));
-      any = true;
-    }
+    if (vec == 4)
+      stream_row<float4, 4>(src, pre2 >> 1, t, [&](const float4& v, int) {
+        fmin_ = fminf(fmin_, fminf(fminf(v.x + 0.f, v.y + 0.f), fminf(v.z + 0.f, v.w + 0.f)));
+        any = true;
+      });
+    else
+      stream_row<float2, 8>(src, pre2, t, [&](const float2& v, int) {
+        fmin_ = fminf(fmin_, fminf(v.x + 0.f, v.y + 0.f));
+        any = true;
+      });
     if (any) tmin = min(tmin, float_key(fmin_));
   }
   for (int j = 2 * pre2 + t; j < pre; j += kTopkThreads) {
@@ -203,21 +233,29 @@ topk_rows_kernel(const float* __restrict__ mat, long long ld, int cols, const fl
       if (p < kTopkCap) s_cand[p] = (static_cast<unsigned long long>(final_key(raw)) << 32) | static_cast<unsigned>(j);
     }
   };
-  if (vec2) {
+  if (vec > 1) {
     // filter in the float domain: key(x) <= key(b) <=> x <= b for canonical non-NaN values (a NaN
     // bound only arises when fewer than k entries are not NaN: then every comparison must pass)
-    const float2* src2 = reinterpret_cast<const float2*>(src);
     const float bound_f = key_float(bound);
     const bool all = bound_f != bound_f;
-#pragma unroll 8
-    for (int j = t; j < cols2; j += kTopkThreads) {
-      const float2 v = __ldg(src2 + j);
-      const float a = v.x + 0.f, b = v.y + 0.f;
-      if (all || a <= bound_f || b <= bound_f) {
-        offer(float_key(a), 2 * j);
-        offer(float_key(b), 2 * j + 1);
-      }
-    }
+    if (vec == 4)
+      stream_row<float4, 4>(src, cols2 >> 1, t, [&](const float4& v, int j) {
+        const float a = v.x + 0.f, b = v.y + 0.f, c = v.z + 0.f, e = v.w + 0.f;
+        if (all || fminf(fminf(a, b), fminf(c, e)) <= bound_f) {
+          offer(float_key(a), 4 * j);
+          offer(float_key(b), 4 * j + 1);
+          offer(float_key(c), 4 * j + 2);
+          offer(float_key(e), 4 * j + 3);
+        }
+      });
+    else
+      stream_row<float2, 8>(src, cols2, t, [&](const float2& v, int j) {
+        const float a = v.x + 0.f, b = v.y + 0.f;
+        if (all || a <= bound_f || b <= bound_f) {
+          offer(float_key(a), 2 * j);
+          offer(float_key(b), 2 * j + 1);
+        }
+      });
   }
   for (int j = 2 * cols2 + t; j < cols; j += kTopkThreads) offer(raw_at(j), j);
   __syncthreads();
@@ -697,7 +735,7 @@ int launch_topk_rows(const float* mat, long long ld, int rows, int cols, const f
     // prefix for the bound: the expected number of candidates of the filter pass is about
     // (cols / prefix) * 64 * ln(64 / (64 - k)) (k-th smallest of 64 group minima); keep it near
     // half the candidate buffer.  k > 63 uses 256 single-thread groups and the whole row.
-    // Rows up to ~12k columns are re-read from L2 by the filter pass (8 resident blocks per SM keep
+    // Rows up to ~12k columns are re-read from L2 by the filter pass (resident blocks keep
     // < 64 MB in flight); beyond that the second pass would come from HBM again.
     int prefix = cols;
     if (k < 64 && cols > 12288) {

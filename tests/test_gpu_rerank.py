@@ -135,6 +135,26 @@ def test_row_sharded_reranking_is_bit_identical(shape, k1, k2, ranks):
     assert torch.equal(whole, sharded)
 
 
+@pytest.mark.parametrize("cols,k", [(7001, 21), (8000, 51), (10290, 21), (10291, 51), (12288, 63)])
+def test_topk_mid_rows(cols, k):
+    """Rows of 6k..12k columns (re-ranking at RGBNT100 scale): bound from a prefix of >= 4096 entries,
+    16-/8-/4-byte load paths by row alignment, ties, +-inf, smallest entries outside the prefix."""
+    from demo2_b200 import reranking
+    rng = np.random.default_rng(cols + k)
+    m = rng.random((16, cols), dtype=np.float32)
+    m[2] = np.round(m[2] * 40) / 40            # massive ties -> radix fallback
+    m[4, :5000] += 1.0                         # the prefix holds only large values: loose bound
+    m[6] = np.sort(m[6])[::-1]                 # the smallest entries sit at the very end
+    m[8, ::3] = np.inf
+    m[9, 100:200] = -np.inf
+    m[10] = -m[10]
+    m[10, 5] = 0.0
+    m[10, 7] = -0.0                            # -0 ties with +0, lower column first
+    idx = reranking.topk_rows(torch.from_numpy(m).cuda(), k).cpu().numpy()
+    ref = np.argsort(m, axis=1, kind="stable")[:, :k]
+    np.testing.assert_array_equal(idx, ref)
+
+
 @pytest.mark.parametrize("cols,k", [(100000, 21), (100000, 50), (70001, 63), (100000, 100), (40000, 5)])
 def test_topk_long_rows(cols, k):
     """Rows longer than the shared-memory cache: the selection bound comes from a row prefix and

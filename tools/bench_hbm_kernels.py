@@ -58,6 +58,12 @@ for R, C, k in ((10290, 10290, 21), (4096, 262144, 50), (16384, 65536, 21)):
     m = torch.rand(R, C, device=dev, generator=gen)
     ms = timed(lambda: reranking.topk_rows(m, k))
     report("topk_rows %d x %d, k=%d" % (R, C, k), ms, R * C * 4)
+    if C == 10290:   # the all-pairs matrix of the re-ranking path has a 128-byte row pitch: every row 16-byte aligned
+        for kk in (21, 51):
+            mp = torch.rand(R, 10304, device=dev, generator=gen)[:, :C]
+            ms = timed(lambda: reranking.topk_rows(mp, kk))
+            report("topk_rows %d x %d (row pitch 10304), k=%d" % (R, C, kk), ms, R * C * 4)
+        del mp
     del m
 
 # rank counts over a materialised matrix (eval_func on a distance matrix): 4 B per pair read once
