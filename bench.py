@@ -595,6 +595,31 @@ def other_workloads(dev, peaks):
         ms, r = timed(rr, iters=5)
         entry = {"ms": ms, "queries_per_s": Q / ms * 1e3, "mAP": float(r.mAP),
                  "config": "BASELINE.json configs[%d]" % cfg}
+        # the parameters R1_mAP_eval.compute hard-codes (utils/metrics.py:244: k1=50, k2=15)
+        ms50, _ = timed(lambda: reranking.re_ranking_device(qf, gf, 50, 15, 0.3, normalize=True), iters=5)
+        entry["re_ranking_k50_15_ms"] = ms50
+        # re_ranking alone, eager and as ONE CUDA-graph replay (the ~14 launches of the call are
+        # launch-latency-bound at this size; the library call itself has no host synchronisation)
+        try:
+            ms_e, eager = timed(lambda: reranking.re_ranking_device(qf, gf, 20, 6, 0.3, normalize=True), iters=10)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    reranking.re_ranking_device(qf, gf, 20, 6, 0.3, normalize=True)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = reranking.re_ranking_device(qf, gf, 20, 6, 0.3, normalize=True)
+            graph.replay()
+            torch.cuda.synchronize()
+            ms_g, _ = timed(graph.replay, iters=20)
+            entry["re_ranking_k20_6"] = {"eager_ms": ms_e, "graphed_ms": ms_g,
+                                         "graphed_matches_eager": bool(torch.equal(static_out, eager))}
+            del graph, static_out
+        except Exception as exc:
+            entry["re_ranking_k20_6"] = {"graphed_error": repr(exc)}
         # HBM-bound kernels of this config on their own (algorithmic bytes / CUDA-event time)
         allp = metrics.sqdist_device(torch.cat([qf, gf]), torch.cat([qf, gf]), normalize=True)
         ms_k, _ = timed(lambda: reranking.topk_rows(allp, 21), iters=20)
