@@ -409,7 +409,7 @@ recip_half_kernel(const int* __restrict__ rank, int K, int N, int kh, int* __res
   if (lane == 0) rh_cnt[c] = n;
 }
 
-__global__ void __launch_bounds__(kKrThreads)
+__global__ void __launch_bounds__(kKrThreads, 16)
 krecip_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ rowmax,
               const int* __restrict__ rank, int K, int N, int k1, int kh, int cap, int* __restrict__ v_idx,
               __half* __restrict__ v_val, int* __restrict__ v_cnt, int row0, const int* __restrict__ rh_idx,
@@ -765,6 +765,16 @@ int rerank_capq(int N, int k1, int k2) {
 
 constexpr size_t kJcMaxSmemTmin = 200 * 1024;
 constexpr int kJcPackedRows = 65536;   // gallery rows a one-word inverted-list entry can address
+// The two large-problem variants (two-word entries beyond 65 536 gallery rows, temp_min in global
+// memory beyond ~100 000) can be forced at any size, so that tests reach them without a 17 GB matrix.
+static bool jc_packed(size_t G) {
+  static const bool force_wide = getenv("DEMO_JC_WIDE") != nullptr;
+  return G <= static_cast<size_t>(kJcPackedRows) && !force_wide;
+}
+static bool jc_scratch(size_t G) {
+  static const bool force_scratch = getenv("DEMO_JC_SCRATCH") != nullptr;
+  return G * 2 > kJcMaxSmemTmin || force_scratch;
+}
 
 template <typename Ent, int kAhead>
 static int launch_jaccard_t(int nq, size_t smem, cudaStream_t stream, const float* E, long long lde, const float* rowmax,
@@ -786,7 +796,7 @@ static int launch_index_and_jaccard(const float* E, long long lde, const float* 
                                     cudaStream_t stream) {
   const int G = N - Q;
   DEMO_REQUIRE(G >= 1, "re_ranking: empty gallery");
-  const bool packed = G <= kJcPackedRows;
+  const bool packed = jc_packed(G);
   DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
   DEMO_CHECK_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int) * (N + 1), stream));
   inv_count_kernel<<<G, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, Q, w.col_cnt);
@@ -810,6 +820,9 @@ static int launch_index_and_jaccard(const float* E, long long lde, const float* 
   static const int force = getenv("DEMO_JC_AHEAD") ? atoi(getenv("DEMO_JC_AHEAD")) : 0;   // A/B experiments
   // measured at 50 / 15 (lists of ~480 gallery rows): depth 2 0.77 ms, depth 3 0.80 ms, depth 1 (round 1) 1.07 ms
   const int ahead = force ? force : est <= 0.8 * kJcThreads ? 1 : est <= 3.0 * kJcThreads ? 2 : 3;
+  // (128-thread blocks for the short lists of k1 = 20 / k2 = 6 -- 3 of 8 warps have entries there --
+  // measured the same 0.098 ms: at that size half of the kernel's instructions are the two IEEE
+  // divisions per output element of the blend epilogue, not the column walk.)
 #define DEMO_JC(ENT, A) \
   return launch_jaccard_t<ENT, A>(nq, smem, stream, E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w, oml, lam, out, ldo, row0)
   if (packed) {
@@ -842,14 +855,14 @@ size_t rerank_carve(Carver& c, int N, int Q, int k1, int k2, RerankWs* w) {
   t.col_cnt = c.take<int>(n + 1);
   t.inv_ofs = c.take<int>(n + 1);
   t.cursor = c.take<int>(n + 1);
-  t.inv_ent = c.take<unsigned>(g * t.capq * (g <= static_cast<size_t>(kJcPackedRows) ? 1 : 2));
+  t.inv_ent = c.take<unsigned>(g * t.capq * (jc_packed(g) ? 1 : 2));
   size_t tmp = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp, t.col_cnt, t.inv_ofs, N + 1);
   t.cub_bytes = tmp + 256;
   t.cub_tmp = c.take<char>(t.cub_bytes);
   t.tmin_scratch = nullptr;
   t.tmin_bytes = 0;
-  if (g * 2 > kJcMaxSmemTmin) {  // temp_min (gallery rows) does not fit shared memory
+  if (jc_scratch(g)) {  // temp_min (gallery rows) does not fit shared memory
     const size_t q = Q > 0 ? Q : 1;
     t.tmin_bytes = q * g * 2;
     t.tmin_scratch = c.take<__half>(q * g);

@@ -168,3 +168,25 @@ def test_topk_long_rows(cols, k):
     idx = reranking.topk_rows(torch.from_numpy(m).cuda(), k).cpu().numpy()
     ref = np.argsort(m, axis=1, kind="stable")[:, :k]
     np.testing.assert_array_equal(idx, ref)
+
+
+@pytest.mark.parametrize("k1,k2", [(20, 6), (50, 15), (20, 1)])
+def test_rerank_large_problem_variants_are_bit_identical(R, tmp_path, k1, k2):
+    """The Jaccard variants for problems too large to test directly (two-word inverted-list entries
+    beyond 65 536 gallery rows, temp_min in global memory beyond ~100 000): forced at a small size
+    in a fresh process, the result must equal the default path's bit for bit."""
+    import os
+    import subprocess
+    import sys
+    qf, gf, *_ = make_case("rgbnt201", 0, 5.0)
+    qf, gf = qf[:300], gf[:700]
+    ours = R.re_ranking(qf, gf, k1, k2, 0.3)
+    np.save(tmp_path / "q.npy", qf)
+    np.save(tmp_path / "g.npy", gf)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from demo2_b200 import reranking as R; "
+            "np.save(%r, R.re_ranking(np.load(%r), np.load(%r), %d, %d, 0.3))"
+            % (root, str(tmp_path / "out.npy"), str(tmp_path / "q.npy"), str(tmp_path / "g.npy"), k1, k2))
+    env = dict(os.environ, DEMO_JC_WIDE="1", DEMO_JC_SCRATCH="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    np.testing.assert_array_equal(np.load(tmp_path / "out.npy"), ours)
