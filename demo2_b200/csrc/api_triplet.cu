@@ -77,6 +77,8 @@ __global__ void mining_matrix_kernel(const float* __restrict__ dm, long long ld,
   }
 }
 
+constexpr int kTripletMaxN = 12800;   // 200 KB of per-anchor coefficients in the backward kernel
+
 // grad_x[r] = sum over anchors a of the pair terms that touch row r (deterministic gather form):
 //   pair (a, b) with upstream g and distance D contributes  +g (x_a - x_b)/D to row a, - the same to row b;
 //   zero when the clamp was active (D^2 <= 1e-12).
@@ -146,6 +148,8 @@ int demo_triplet_hard_fwd(const float* x, int N, int d, int64_t ld, const int* l
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DEMO_REQUIRE(x && labels && dist_ap && dist_an && p_idx && n_idx && ws && N > 0 && d > 0 && ld >= d,
                "triplet_hard_fwd: bad arguments");
+  // the backward kernel stages 16 B per anchor in shared memory: refuse here what it could not take
+  DEMO_REQUIRE(N <= kTripletMaxN, "triplet_hard_fwd: batch too large (N=%d, max %d)", N, kTripletMaxN);
   Carver c(ws, ws_bytes);
   TripletWs w;
   carve_triplet(c, N, d, &w);
@@ -183,7 +187,9 @@ int demo_triplet_hard_bwd(const float* x, int N, int d, int64_t ld, const int64_
   DEMO_REQUIRE(x && p_idx && n_idx && dist_ap && dist_an && g_ap && g_an && grad_x && N > 0 && d > 0,
                "triplet_hard_bwd: bad arguments");
   const size_t smem = static_cast<size_t>(N) * 16;
-  DEMO_REQUIRE(smem <= 48 * 1024, "triplet_hard_bwd: batch too large (N=%d)", N);
+  DEMO_REQUIRE(N <= kTripletMaxN, "triplet_hard_bwd: batch too large (N=%d, max %d)", N, kTripletMaxN);
+  static PerDeviceInt configured;
+  DEMO_CHECK_CUDA(ensure_dynamic_smem(configured, triplet_bwd_kernel, kTripletMaxN * 16));
   triplet_bwd_kernel<<<N, 256, smem, stream>>>(x, N, d, ld, reinterpret_cast<const long long*>(p_idx),
                                                reinterpret_cast<const long long*>(n_idx), dist_ap, dist_an, g_ap,
                                                g_an, grad_x, ldg);

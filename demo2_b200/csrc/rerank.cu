@@ -493,7 +493,7 @@ constexpr int kQeAcc = 2048;    // output slots accumulated per pass of the expa
 __global__ void __launch_bounds__(kQeThreads)
 expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const int* __restrict__ v_idx,
               const __half* __restrict__ v_val, const int* __restrict__ v_cnt, int capq,
-              int* __restrict__ q_idx, __half* __restrict__ q_val, int* __restrict__ q_cnt, int row0) {
+              int* __restrict__ q_idx, __half* __restrict__ q_val, int* __restrict__ q_cnt, int row0, int acc_slots) {
   extern __shared__ unsigned s_dyn[];
   const int words = ceil_div(N, 32);
   unsigned* bm = s_dyn;
@@ -501,7 +501,7 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
   // fp32 accumulators for kQeAcc output slots at a time (the union of k2 rows has a few hundred
   // entries; its worst-case bound capq = min(N, k2 * cap) used to size TWO shared arrays -- 82 KB
   // at k1 = 50, k2 = 15, N = 10 290, two blocks per SM); the column list goes straight to q_idx
-  float* s_acc = reinterpret_cast<float*>(s_dyn + 2 * words);     // [kQeAcc]
+  float* s_acc = reinterpret_cast<float*>(s_dyn + 2 * words);     // [acc_slots]
   __shared__ unsigned s_scan[kQeThreads + 1];
   __shared__ int s_nb[64], s_cnt[64];
   const int i = blockIdx.x + row0, t = threadIdx.x;
@@ -521,8 +521,8 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
   const int n = bm_enumerate(bm, words, q_idx + (long long)i * capq, capq, s_scan, wp);
   const int nn = min(n, capq);
   const float k2f = static_cast<float>(k2);
-  for (int c0 = 0; c0 < nn; c0 += kQeAcc) {          // one pass unless the union is unusually large
-    const int cn = min(kQeAcc, nn - c0);
+  for (int c0 = 0; c0 < nn; c0 += acc_slots) {       // one pass unless the union is unusually large
+    const int cn = min(acc_slots, nn - c0);
     for (int p = t; p < cn; p += kQeThreads) s_acc[p] = 0.f;
     __syncthreads();
     for (int m = 0; m < k2; ++m) {  // sequential float32 sum in neighbour order (np.mean over fp16 rows)
@@ -932,11 +932,15 @@ int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int
   DEMO_REQUIRE(k2 >= 2 && k2 <= 64 && k2 <= N, "re_ranking: expansion needs 2 <= k2 <= min(N, 64) (k2=%d)", k2);
   if (nrows <= 0) return DEMO_OK;
   const int K = rerank_k(k1, k2), cap = rerank_cap(k1), capq = rerank_capq(N, k1, k2), words = ceil_div(N, 32);
-  const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(kQeAcc) * 4;
+  // DEMO_QE_ACC: tests force the multi-pass accumulation (unions of more than kQeAcc = 2048 columns
+  // do not occur in practice: ~1000 at k1 = 120 / k2 = 64 on adversarial low-dimensional data)
+  static const int acc_env = getenv("DEMO_QE_ACC") ? atoi(getenv("DEMO_QE_ACC")) : 0;
+  const int acc_slots = acc_env >= 32 && acc_env <= kQeAcc ? acc_env : kQeAcc;
+  const size_t smem = static_cast<size_t>(2 * words) * 4 + static_cast<size_t>(acc_slots) * 4;
   DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d too large for the expansion kernel", N);
   DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   expand_kernel<<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx, q_val,
-                                                     q_cnt, row0);
+                                                     q_cnt, row0, acc_slots);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }

@@ -128,8 +128,8 @@ class _FusedHardTriplet(torch.autograd.Function):
         lib = _lib.require_device()
         x = x.contiguous() if x.stride(1) != 1 else x
         N, d = x.shape
-        if N > 3072:   # the backward kernel keeps 16 bytes per anchor in 48 KB of shared memory
-            raise ValueError("fused TripletLoss supports up to 3072 anchors per batch (got %d)" % N)
+        # up to 12 800 anchors: the library refuses larger batches here, in forward (its backward
+        # kernel keeps 16 bytes per anchor in shared memory)
         lab = _labels_i32(labels, x.device)
         ap = torch.empty(N, dtype=torch.float32, device=x.device)
         an = torch.empty(N, dtype=torch.float32, device=x.device)

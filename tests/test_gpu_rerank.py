@@ -173,7 +173,8 @@ def test_topk_long_rows(cols, k):
 @pytest.mark.parametrize("k1,k2", [(20, 6), (50, 15), (20, 1)])
 def test_rerank_large_problem_variants_are_bit_identical(R, tmp_path, k1, k2):
     """The Jaccard variants for problems too large to test directly (two-word inverted-list entries
-    beyond 65 536 gallery rows, temp_min in global memory beyond ~100 000): forced at a small size
+    beyond 65 536 gallery rows, temp_min in global memory beyond ~100 000) and the multi-pass
+    accumulation of the expansion kernel (unions of more than 2048 columns): forced at a small size
     in a fresh process, the result must equal the default path's bit for bit."""
     import os
     import subprocess
@@ -187,6 +188,6 @@ def test_rerank_large_problem_variants_are_bit_identical(R, tmp_path, k1, k2):
     code = ("import sys, numpy as np; sys.path.insert(0, %r); from demo2_b200 import reranking as R; "
             "np.save(%r, R.re_ranking(np.load(%r), np.load(%r), %d, %d, 0.3))"
             % (root, str(tmp_path / "out.npy"), str(tmp_path / "q.npy"), str(tmp_path / "g.npy"), k1, k2))
-    env = dict(os.environ, DEMO_JC_WIDE="1", DEMO_JC_SCRATCH="1")
+    env = dict(os.environ, DEMO_JC_WIDE="1", DEMO_JC_SCRATCH="1", DEMO_QE_ACC="64")   # + multi-pass expansion
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
     np.testing.assert_array_equal(np.load(tmp_path / "out.npy"), ours)

@@ -183,3 +183,26 @@ def test_one_launch_path_ragged_shapes_vs_torch(T, P, K, d, margin, hf):
     # repeated launches reuse the self-resetting workspace
     loss2, _, _ = T.TripletLoss(margin=margin, hard_factor=hf)(x, labels)
     assert loss2.item() == loss.item()
+
+
+def test_large_batch_forward_backward_and_limit(T):
+    """Batches beyond the one-launch path and beyond 3 072 anchors (48 KB of backward coefficients,
+    the old limit that only showed up in backward): forward + backward vs torch fp32; the library
+    refuses in FORWARD what the backward kernel could not take."""
+    torch.manual_seed(3)
+    P, K, d = 500, 8, 64                       # N = 4000
+    labels = torch.arange(P).repeat_interleave(K).cuda()
+    x = torch.randn(P * K, d, device="cuda")
+    xr = x.clone().requires_grad_(True)
+    loss, ap, an = T.TripletLoss(margin=0.3)(xr, labels)
+    loss.backward()
+    xt = x.clone().requires_grad_(True)
+    lt, apt, ant = torch_ref_loss(xt, labels, margin=0.3)
+    lt.backward()
+    np.testing.assert_allclose(loss.item(), lt.item(), rtol=1e-5)
+    np.testing.assert_allclose(ap.detach().cpu().numpy(), apt.detach().cpu().numpy(), rtol=1e-4)
+    np.testing.assert_allclose(an.detach().cpu().numpy(), ant.detach().cpu().numpy(), rtol=1e-4)
+    np.testing.assert_allclose(xr.grad.cpu().numpy(), xt.grad.cpu().numpy(), rtol=2e-3, atol=1e-7)
+    big = torch.randn(12808, 8, device="cuda")
+    with pytest.raises(Exception, match="batch too large"):
+        T.TripletLoss(margin=0.3)(big, torch.arange(12808, device="cuda") // 8)
