@@ -123,7 +123,7 @@ def _worker(rank, world, port, mode, out):
 
 
 def _spawn(mode, world=2):
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()   # never fork a process that holds a CUDA context
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), mode, out), nprocs=world, join=True)
     assert len(out) == world
