@@ -606,6 +606,14 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
     if (pos & 0x80000000u) pos = slow_pos(d, g);
     bump(pos);
   };
+  // Elements beyond the row's last threshold only ever reach bin nthr, which nothing reads (the
+  // final scan adds bins <= k for k < nthr): a vector of four such elements is dropped after three
+  // fminf and one compare.  With a working retrieval model the positives -- the thresholds -- sit at
+  // the head of the ranking and almost every vector goes this way; on adversarial data (thresholds
+  // spread over the whole value range) the test costs ~4 % more instructions.
+  auto beyond = [&](const float4& x) -> bool {
+    return !(fminf(fminf(x.x, x.y), fminf(x.z, x.w)) <= tmax);
+  };
   auto place8 = [&](const float4& x, const float4& y, int g0, int g1) {
     const float d[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
     unsigned pos[8];
@@ -620,6 +628,7 @@ count_matrix255_kernel(const float* __restrict__ distmat, long long ld, int G, i
     for (int k = 0; k < 8; ++k) bump(pos[k]);
   };
   auto place4 = [&](const float4& x, int g0) {
+    if (beyond(x)) return;
     const float d[4] = {x.x, x.y, x.z, x.w};
     unsigned pos[4];
 #pragma unroll
