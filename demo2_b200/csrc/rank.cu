@@ -396,12 +396,13 @@ namespace {
 
 constexpr int kCmThreads = 256;
 constexpr int kCmWin = 2048;  // thresholds handled per pass over the row
+constexpr int kCmSmallG = 12288;   // rows of up to this many columns: bisection kernel for every row (measured: profiles/count_small_rows_r2b.txt)
 
 __global__ void __launch_bounds__(kCmThreads)
 count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int g_index_base,
                     const int* __restrict__ q_perm, const int* __restrict__ thr_ofs,
                     const int* __restrict__ thr_cnt, const float* __restrict__ thr_val,
-                    const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int window, int skip_small,
+                    const int* __restrict__ thr_gidx, unsigned* __restrict__ counts, int window, int take_all,
                     CountRows rows) {
   __shared__ float s_thr[kCmWin];
   __shared__ int s_tg[kCmWin];
@@ -414,7 +415,7 @@ count_matrix_kernel(const float* __restrict__ distmat, long long ld, int G, int 
   const int nthr = max(0, min(kCmWin, thr_cnt[i] - window * kCmWin));
   if (nthr == 0) return;
   // rows with <= 255 finite thresholds belong to count_matrix255_kernel
-  if (thr_cnt[i] <= 255 && isfinite(thr_val[thr_ofs[i] + thr_cnt[i] - 1])) return;
+  if (!take_all && thr_cnt[i] <= 255 && isfinite(thr_val[thr_ofs[i] + thr_cnt[i] - 1])) return;
   for (int k = t; k < nthr; k += kCmThreads) {
     s_thr[k] = thr_val[tbase + k];
     s_tg[k] = thr_gidx[tbase + k];
@@ -723,8 +724,13 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
   static_assert(kCmWin == kCmThreads * 8, "scan layout");
   CountRows rows;
   if (rows_) rows = *rows_;
+  // Short rows: the arithmetic-bin kernel's per-row set-up (4096-bin table, 16-48 KB of private
+  // histogram columns) costs more than it saves; below kSmallG columns every row goes to the
+  // bisection kernel (per-element early-out beyond the last threshold, shared-memory atomics).
+  static const int small_g = getenv("DEMO_CM_SMALL_G") ? atoi(getenv("DEMO_CM_SMALL_G")) : kCmSmallG;
+  const bool all_generic = G <= small_g;
   // rows with up to 255 finite thresholds
-  {
+  if (!all_generic) {
     // histogram rows: one per slot of the longest row this kernel takes (more resident blocks for short lists)
     const int top = max_cnt < kC8Bins - 1 ? (max_cnt > 0 ? max_cnt : 1) : kC8Bins - 1;
     const int hist_rows = (top + 1 + 31) / 32 * 32 < 64 ? 64 : (top + 1 + 31) / 32 * 32;   // >= 4 rows: setup scratch
@@ -739,7 +745,7 @@ int launch_count_matrix(const float* distmat, long long ld, int G, int g_index_b
   const int windows = ceil_div(max_cnt > 0 ? max_cnt : 1, kCmWin);
   for (int w = 0; w < windows; ++w) {
     count_matrix_kernel<<<Q, kCmThreads, 0, stream>>>(distmat, ld, G, g_index_base, q_perm, thr_ofs, thr_cnt,
-                                                      thr_val, thr_gidx, counts, w, 0, rows);
+                                                      thr_val, thr_gidx, counts, w, all_generic ? 1 : 0, rows);
     DEMO_CHECK_CUDA(cudaGetLastError());
   }
   return DEMO_OK;
