@@ -602,7 +602,10 @@ __global__ void inv_fill_kernel(const int* __restrict__ idx, const __half* __res
 // walks the columns alone with __syncwarp only -- 1.10 ms instead of 1.07 ms at k1 = 50 / k2 = 15
 // and 0.24 instead of 0.115 ms at 20 / 6: the kernel is bound by shared-memory wavefronts (a
 // read-modify-write of 32 random fp16 slots costs ~7 of them), not by the barriers, and the
-// per-class lists fill the lanes worse.
+// per-class lists fill the lanes worse.  Also measured and reverted: the gallery rows of a query cut
+// into S ranges with their own inverted lists and one block per (query, range) -- 0.76 ms (S = 1),
+// 0.92 ms (S = 2), 1.32 ms (S = 4) at 50 / 15: the time follows the number of (block, column)
+// steps, i.e. the per-column barrier and metadata reads, not the entries per column.
 // ---------------------------------------------------------------------------------------
 constexpr int kJcThreads = 256;
 constexpr int kJcChunk = 512;   // columns staged per round
