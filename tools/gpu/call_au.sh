@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
+  --log-file gpurun_out/launches_rerank5015_r2au.csv python tools/profile_rerank_50_15.py > /dev/null 2>&1
+(timeout 600 python -m pytest tests/test_gpu_rerank.py -m gpu -q -x -k "stages or variants or sharded" 2>&1 | tail -2)
