@@ -590,6 +590,25 @@ __global__ void inv_fill_kernel(const int* __restrict__ idx, const __half* __res
   }
 }
 
+// The Jaccard term of the blend, fp16((1 - t / (2 - t)) * fp16(1 - lambda)) with numpy's half
+// arithmetic, is a function of the 16-bit temp_min value alone: tabulated once per call for
+// t in [0, 2) (bit patterns 0 .. 0x3fff; temp_min is a sum of minima of weights that add up to ~1).
+// At k1 = 20 / k2 = 6 half of the Jaccard kernel's instructions were the blend epilogue's two IEEE
+// divisions and five half roundings per output element; the table leaves one division.
+constexpr int kJacTab = 0x4000;
+__device__ __forceinline__ float jaccard_term(__half tm, __half w) {
+  const __half one = __float2half_rn(1.f), two = __float2half_rn(2.f);
+  const __half jac = np_hsub(one, np_hdiv(tm, np_hsub(two, tm)));           // 1 - tmin / (2 - tmin)
+  return __half2float(np_hmul(jac, w));
+}
+// out-of-table values (t >= 2: not reachable from normalised weights) -- kept out of line so that the
+// epilogue's unrolled body stays small
+__device__ __noinline__ float jaccard_term_slow(__half tm, __half w) { return jaccard_term(tm, w); }
+__global__ void jaccard_table_kernel(float one_minus_lambda_h, float* __restrict__ tab) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < kJacTab) tab[b] = jaccard_term(__ushort_as_half(static_cast<unsigned short>(b)), __float2half_rn(one_minus_lambda_h));
+}
+
 // ---------------------------------------------------------------------------------------
 // Jaccard distance + blend (one block per query row).
 // temp_min[t] receives, for ascending columns j of V[i], fp16(temp_min[t] + min(V[i,j], V[t,j]))
@@ -611,13 +630,13 @@ constexpr int kJcThreads = 256;
 constexpr int kJcChunk = 512;   // columns staged per round
 constexpr int kJcGroup = 8;     // columns whose entries are fetched together
 
-template <typename Ent, int kAhead>
-__global__ void __launch_bounds__(kJcThreads, kAhead == 1 ? 8 : kAhead == 2 ? 6 : 4)   // depth 2: 40 registers without spills; 32 (8 blocks) spills in the column loop: 1.22 ms instead of 0.72
+template <typename Ent, int kAhead, int kMinBlocks>
+__global__ void __launch_bounds__(kJcThreads, kMinBlocks)
 jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ rowmax, int N, int Q,
                const int* __restrict__ idx, const __half* __restrict__ val, const int* __restrict__ cnt, int cap,
                const int* __restrict__ inv_ofs, const Ent* __restrict__ inv_ent,
                float one_minus_lambda_h, float lambda_f, __half* __restrict__ scratch, float* __restrict__ out,
-               long long ldo, int row0) {
+               long long ldo, int row0, const float* __restrict__ jac_tab) {
   extern __shared__ __half s_tmin[];
   __shared__ int s_beg[kJcChunk], s_len[kJcChunk];
   __shared__ __half s_v[kJcChunk];
@@ -678,7 +697,6 @@ jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restri
     }
   }
   __syncthreads();
-  const __half one = __float2half_rn(1.f), two = __float2half_rn(2.f);
   const __half w = __float2half_rn(one_minus_lambda_h);
   const float div = rowmax[li];
   // 8 independent row loads in flight per thread: with 64 KB of temp_min per block only three blocks
@@ -697,9 +715,10 @@ jaccard_kernel(const float* __restrict__ E, long long lde, const float* __restri
       const int g = g0 + u * kJcThreads;
       if (g >= G) break;
       const __half tm = tmin[g];
-      const __half jac = np_hsub(one, np_hdiv(tm, np_hsub(two, tm)));           // 1 - tmin / (2 - tmin)
+      const unsigned tb = __half_as_ushort(tm);
+      const float jt = tb < static_cast<unsigned>(kJacTab) ? __ldg(jac_tab + tb) : jaccard_term_slow(tm, w);
       const float od = e[u] / div;
-      __stcs(orow + g, __fadd_rn(__half2float(np_hmul(jac, w)), __fmul_rn(od, lambda_f)));  // (:95), no FMA contraction
+      __stcs(orow + g, __fadd_rn(jt, __fmul_rn(od, lambda_f)));  // (:95), no FMA contraction
     }
   }
 }
@@ -779,14 +798,16 @@ static bool jc_scratch(size_t G) {
   return G * 2 > kJcMaxSmemTmin || force_scratch;
 }
 
-template <typename Ent, int kAhead>
+template <typename Ent, int kAhead, int kMinBlocks>
 static int launch_jaccard_t(int nq, size_t smem, cudaStream_t stream, const float* E, long long lde, const float* rowmax,
                             int N, int Q, const int* f_idx, const __half* f_val, const int* f_cnt, int f_cap,
                             const RerankWs& w, float oml, float lambda_f, float* out, long long ldo, int row0) {
-  auto kern = jaccard_kernel<Ent, kAhead>;
+  auto kern = jaccard_kernel<Ent, kAhead, kMinBlocks>;
   DEMO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kJcMaxSmemTmin)));
+  jaccard_table_kernel<<<kJacTab / 256, 256, 0, stream>>>(oml, w.jac_tab);
   kern<<<nq, kJcThreads, smem, stream>>>(E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w.inv_ofs,
-                                         static_cast<const Ent*>(w.inv_ent), oml, lambda_f, w.tmin_scratch, out, ldo, row0);
+                                         static_cast<const Ent*>(w.inv_ent), oml, lambda_f, w.tmin_scratch, out, ldo, row0,
+                                         w.jac_tab);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }
@@ -826,16 +847,18 @@ static int launch_index_and_jaccard(const float* E, long long lde, const float* 
   // (128-thread blocks for the short lists of k1 = 20 / k2 = 6 -- 3 of 8 warps have entries there --
   // measured the same 0.098 ms: at that size half of the kernel's instructions are the two IEEE
   // divisions per output element of the blend epilogue, not the column walk.)
-#define DEMO_JC(ENT, A) \
-  return launch_jaccard_t<ENT, A>(nq, smem, stream, E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w, oml, lam, out, ldo, row0)
+  // resident blocks per SM: 6 for depth 1 and 2 (40 registers, no spills; depth 1 at 8 blocks = 32 registers
+  // spills: 0.092 instead of 0.082 ms at 20 / 6, depth 2 at 8 blocks: 1.22 instead of 0.72 ms at 50 / 15)
+#define DEMO_JC(ENT, A, B) \
+  return launch_jaccard_t<ENT, A, B>(nq, smem, stream, E, lde, rowmax, N, Q, f_idx, f_val, f_cnt, f_cap, w, oml, lam, out, ldo, row0)
   if (packed) {
-    if (ahead == 1) DEMO_JC(unsigned, 1);
-    if (ahead == 2) DEMO_JC(unsigned, 2);
-    DEMO_JC(unsigned, 3);
+    if (ahead == 1) DEMO_JC(unsigned, 1, 6);
+    if (ahead == 2) DEMO_JC(unsigned, 2, 6);
+    DEMO_JC(unsigned, 3, 4);
   }
-  if (ahead == 1) DEMO_JC(JcWide, 1);
-  if (ahead == 2) DEMO_JC(JcWide, 2);
-  DEMO_JC(JcWide, 3);
+  if (ahead == 1) DEMO_JC(JcWide, 1, 5);   // two-word entries: 48 / 64 registers without spills
+  if (ahead == 2) DEMO_JC(JcWide, 2, 4);
+  DEMO_JC(JcWide, 3, 3);
 #undef DEMO_JC
 }
 
@@ -859,6 +882,7 @@ size_t rerank_carve(Carver& c, int N, int Q, int k1, int k2, RerankWs* w) {
   t.inv_ofs = c.take<int>(n + 1);
   t.cursor = c.take<int>(n + 1);
   t.inv_ent = c.take<unsigned>(g * t.capq * (jc_packed(g) ? 1 : 2));
+  t.jac_tab = c.take<float>(kJacTab);
   size_t tmp = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp, t.col_cnt, t.inv_ofs, N + 1);
   t.cub_bytes = tmp + 256;

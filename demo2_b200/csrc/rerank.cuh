@@ -21,6 +21,7 @@ struct RerankWs {
   int* cursor = nullptr;     // [N+1]
   void* inv_ent = nullptr;   // [(N-Q)*capq] inverted-list entries of the gallery rows: (row - Q) << 16 | fp16 weight
                              // in one word, or two words (row - Q, weight) for more than 65 536 gallery rows
+  float* jac_tab = nullptr;  // [16384] Jaccard term of the blend per temp_min bit pattern (jaccard_table_kernel)
   void* cub_tmp = nullptr;
   size_t cub_bytes = 0;
   __half* tmin_scratch = nullptr;  // [Q][N-Q] only when (N-Q)*2 bytes exceed shared memory
