@@ -494,6 +494,7 @@ krecip_kernel(const float* __restrict__ E, long long lde, const float* __restric
 // ---------------------------------------------------------------------------------------
 constexpr int kQeThreads = 128;
 constexpr int kQeAcc = 2048;    // output slots accumulated per pass of the expansion kernel
+constexpr int kQeGroup = 8;     // neighbour rows whose entries are fetched together
 
 // The union of the k2 neighbour rows is built as a bitmap (= sorted unique columns); the weights are
 // then SCATTERED into their output slot, found by a rank query on the bitmap (per-word prefix +
@@ -535,17 +536,39 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
     const int cn = min(acc_slots, nn - c0);
     for (int p = t; p < cn; p += kQeThreads) s_acc[p] = 0.f;
     __syncthreads();
-    for (int m = 0; m < k2; ++m) {  // sequential float32 sum in neighbour order (np.mean over fp16 rows)
-      const int r = s_nb[m];
-      const int cnt = s_cnt[m];
-      for (int p = t; p < cnt; p += kQeThreads) {
-        const float v = __half2float(v_val[(long long)r * cap + p]);
-        if (v == 0.f) continue;
-        const int c = v_idx[(long long)r * cap + p];
-        const unsigned pos = wp[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u)) - static_cast<unsigned>(c0);
-        if (pos < static_cast<unsigned>(cn)) s_acc[pos] += v;   // columns of one row are distinct: no conflict
+    // sequential float32 sum in neighbour order (np.mean over fp16 rows): one barrier per neighbour
+    // row.  The first entry per thread of kQeGroup rows is fetched BEFORE their barriers, so that a
+    // barrier interval holds shared-memory work only (a V row rarely has more than 128 entries).
+    auto add = [&](float v, int c) {
+      const unsigned pos = wp[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u)) - static_cast<unsigned>(c0);
+      if (pos < static_cast<unsigned>(cn)) s_acc[pos] += v;   // columns of one row are distinct: no conflict
+    };
+    for (int m0 = 0; m0 < k2; m0 += kQeGroup) {
+      float v8[kQeGroup];
+      int c8[kQeGroup];
+#pragma unroll
+      for (int u = 0; u < kQeGroup; ++u) {
+        const int m = m0 + u;
+        v8[u] = 0.f;
+        c8[u] = 0;
+        if (m < k2 && t < s_cnt[m]) {
+          const long long e = (long long)s_nb[m] * cap + t;
+          v8[u] = __half2float(v_val[e]);
+          c8[u] = v_idx[e];
+        }
       }
-      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < kQeGroup; ++u) {
+        const int m = m0 + u;
+        if (m >= k2) break;
+        if (v8[u] != 0.f) add(v8[u], c8[u]);
+        const int cnt = s_cnt[m];
+        for (int p = t + kQeThreads; p < cnt; p += kQeThreads) {   // longer rows
+          const float v = __half2float(v_val[(long long)s_nb[m] * cap + p]);
+          if (v != 0.f) add(v, v_idx[(long long)s_nb[m] * cap + p]);
+        }
+        __syncthreads();
+      }
     }
     for (int p = t; p < cn; p += kQeThreads)
       q_val[(long long)i * capq + c0 + p] = __float2half_rn(s_acc[p] / k2f);
