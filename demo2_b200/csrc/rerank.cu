@@ -504,7 +504,8 @@ constexpr int kQeGroup = 8;     // neighbour rows whose entries are fetched toge
 __global__ void __launch_bounds__(kQeThreads)
 expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const int* __restrict__ v_idx,
               const __half* __restrict__ v_val, const int* __restrict__ v_cnt, int capq,
-              int* __restrict__ q_idx, __half* __restrict__ q_val, int* __restrict__ q_cnt, int row0, int acc_slots) {
+              int* __restrict__ q_idx, __half* __restrict__ q_val, int* __restrict__ q_cnt, int row0, int acc_slots,
+              int* __restrict__ col_cnt, int count_from) {
   extern __shared__ unsigned s_dyn[];
   const int words = ceil_div(N, 32);
   unsigned* bm = s_dyn;
@@ -570,8 +571,14 @@ expand_kernel(const int* __restrict__ rank, int K, int N, int k2, int cap, const
         __syncthreads();
       }
     }
-    for (int p = t; p < cn; p += kQeThreads)
-      q_val[(long long)i * capq + c0 + p] = __float2half_rn(s_acc[p] / k2f);
+    // col_cnt (one-GPU flow): the list lengths of the inverted index over the gallery rows are
+    // counted here, where the entries are produced, instead of by a pass of their own
+    const bool counted = col_cnt != nullptr && i >= count_from;
+    for (int p = t; p < cn; p += kQeThreads) {
+      const __half h = __float2half_rn(s_acc[p] / k2f);
+      q_val[(long long)i * capq + c0 + p] = h;
+      if (counted && __half2float(h) != 0.f) atomicAdd(&col_cnt[q_idx[(long long)i * capq + c0 + p]], 1);
+    }
     __syncthreads();
   }
   if (t == 0) q_cnt[i] = nn;
@@ -850,13 +857,15 @@ static int launch_jaccard_t(int nq, size_t smem, cudaStream_t stream, const floa
 static int launch_index_and_jaccard(const float* E, long long lde, const float* rowmax, int N, int Q, int k1, int k2,
                                     double lambda_value, int row0, int nq, const int* f_idx, const __half* f_val,
                                     const int* f_cnt, int f_cap, const RerankWs& w, float* out, long long ldo,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, bool counted = false) {
   const int G = N - Q;
   DEMO_REQUIRE(G >= 1, "re_ranking: empty gallery");
   const bool packed = jc_packed(G);
-  DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
   DEMO_CHECK_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int) * (N + 1), stream));
-  inv_count_kernel<<<G, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, Q, w.col_cnt);
+  if (!counted) {   // counted: the expansion kernel has already filled col_cnt (run_rerank_stages)
+    DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
+    inv_count_kernel<<<G, 128, 0, stream>>>(f_idx, f_val, f_cnt, f_cap, Q, w.col_cnt);
+  }
   size_t tmp = w.cub_bytes;
   DEMO_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.col_cnt, w.inv_ofs, N + 1, stream));
   if (packed)
@@ -951,14 +960,18 @@ int run_rerank_stages(const float* E, long long lde, const float* rowmax, int N,
   const __half* f_val = w.v_val;
   const int* f_cnt = w.v_cnt;
   int f_cap = w.cap;
+  const bool counted = k2 != 1;
   if (k2 != 1) {
-    DEMO_TRY(launch_expand_rows(w.rank, N, k1, k2, 0, N, w.v_idx, w.v_val, w.v_cnt, w.q_idx, w.q_val, w.q_cnt, stream));
+    DEMO_CHECK_CUDA(cudaMemsetAsync(w.col_cnt, 0, sizeof(int) * (N + 1), stream));
+    DEMO_TRY(launch_expand_rows(w.rank, N, k1, k2, 0, N, w.v_idx, w.v_val, w.v_cnt, w.q_idx, w.q_val, w.q_cnt, stream,
+                                w.col_cnt, Q));
     f_idx = w.q_idx;
     f_val = w.q_val;
     f_cnt = w.q_cnt;
     f_cap = w.capq;
   }
-  DEMO_TRY(launch_index_and_jaccard(E, lde, rowmax, N, Q, k1, k2, lambda_value, 0, Q, f_idx, f_val, f_cnt, f_cap, w, out, ldo, stream));
+  DEMO_TRY(launch_index_and_jaccard(E, lde, rowmax, N, Q, k1, k2, lambda_value, 0, Q, f_idx, f_val, f_cnt, f_cap, w, out, ldo,
+                                    stream, counted));
   return DEMO_OK;
 }
 
@@ -988,7 +1001,7 @@ int launch_krecip_rows(const float* E, long long lde, const float* rowmax, const
 
 int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int nrows, const int* v_idx,
                        const __half* v_val, const int* v_cnt, int* q_idx, __half* q_val, int* q_cnt,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int* col_cnt, int count_from) {
   DEMO_REQUIRE(k2 >= 2 && k2 <= 64 && k2 <= N, "re_ranking: expansion needs 2 <= k2 <= min(N, 64) (k2=%d)", k2);
   if (nrows <= 0) return DEMO_OK;
   const int K = rerank_k(k1, k2), cap = rerank_cap(k1), capq = rerank_capq(N, k1, k2), words = ceil_div(N, 32);
@@ -1000,7 +1013,7 @@ int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int
   DEMO_REQUIRE(smem <= 200 * 1024, "re_ranking: N=%d too large for the expansion kernel", N);
   DEMO_CHECK_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   expand_kernel<<<nrows, kQeThreads, smem, stream>>>(rank_all, K, N, k2, cap, v_idx, v_val, v_cnt, capq, q_idx, q_val,
-                                                     q_cnt, row0, acc_slots);
+                                                     q_cnt, row0, acc_slots, col_cnt, count_from);
   DEMO_CHECK_CUDA(cudaGetLastError());
   return DEMO_OK;
 }

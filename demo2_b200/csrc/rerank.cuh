@@ -48,7 +48,7 @@ int launch_krecip_rows(const float* E, long long lde, const float* rowmax, const
                        int* rh_cnt, cudaStream_t stream);
 int launch_expand_rows(const int* rank_all, int N, int k1, int k2, int row0, int nrows, const int* v_idx,
                        const __half* v_val, const int* v_cnt, int* q_idx, __half* q_val, int* q_cnt,
-                       cudaStream_t stream);
+                       cudaStream_t stream, int* col_cnt = nullptr, int count_from = 0);
 int launch_jaccard_rows(const float* E, long long lde, const float* rowmax, int N, int Q, int k1, int k2, double lambda_value,
                         int row0, int nq_local, const int* f_idx, const __half* f_val, const int* f_cnt, int f_cap,
                         const RerankWs& w, float* out, long long ldo, cudaStream_t stream);
